@@ -1,0 +1,341 @@
+// Persistent warp-specialised bf16 GEMM on tcgen05 / TMEM, operands staged by TMA (128B swizzle).
+//
+//   D[m,n] = epilogue( sum_k A[m,k] * B[n,k] )
+//
+// Replaces every nn.Linear / einsum-free contraction the reference reaches through cuBLAS sgemm:
+//   qkv / proj  (model/video_transformer.py:88-89,103,135), Mlp.fc1/fc2 (:41-52), patch-embed conv-as-GEMM
+//   (:70,76), DistilBERT q/k/v/out_lin + ffn (transformers modeling_distilbert.py), projections
+//   (model/model.py:72-79) and all their backward dgrad / wgrad contractions (autograd in the reference).
+//
+// Layout: A and B are bf16 in HBM.  "K-major" = the contraction index is contiguous (x[M,K], W[N,K]);
+// "MN-major" = the m/n index is contiguous (stored [K, M] / [K, N]) which is what dgrad (W as B) and wgrad
+// (dy and x as A and B, contraction over tokens) need -- no transposed copies are ever materialised.
+// One CTA per SM, 128 x BLOCK_N output tile, 64-deep k-blocks, 4-6 stage TMA->smem ring, fp32 accumulators
+// double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..11 = epilogue.
+#include "common.cuh"
+#include "egovlp_b200.h"
+
+namespace egovlp {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // one 64(mn) x BLOCK_K(k) MN-major slab
+
+struct EpiParams {
+  const float* bias;
+  const float* residual;
+  const bf16* aux;
+  void* out;
+  bf16* out2;
+  long long ldr, ldaux, ldo, ldo2;
+  int out_mode;  // 0 bf16 store, 1 fp32 store, 2 fp32 atomic add
+  int act;       // 0 none, 1 gelu(erf), 2 multiply by gelu'(aux)
+  float alpha;
+  float col_scale;
+  int col_scale_ncols;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
+                         int K, int num_m_blocks, int num_n_blocks, int kb_per_split, int num_splits, EpiParams ep) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bars = sB + STAGES * C::B_STAGE_BYTES;
+  const uint32_t full_bar = bars;                    // STAGES x 8B
+  const uint32_t empty_bar = bars + 8 * STAGES;      // STAGES x 8B
+  const uint32_t tfull_bar = bars + 16 * STAGES;     // 2 x 8B
+  const uint32_t tempty_bar = tfull_bar + 16;        // 2 x 8B
+  const uint32_t tmem_slot = tempty_bar + 16;        // 4B
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = num_m_blocks * num_n_blocks;
+  const int num_units = num_tiles * num_splits;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        const int split = unit / num_tiles, tile = unit - split * num_tiles;
+        const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+        const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, A_STAGE_BYTES + C::B_STAGE_BYTES);
+          const uint32_t a_dst = sA + stage * A_STAGE_BYTES, b_dst = sB + stage * C::B_STAGE_BYTES;
+          if (!A_MN) {
+            tma_load_2d(a_dst, &tmA, fb, kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(a_dst + i * MN_ATOM_BYTES, &tmA, fb, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+          }
+          if (!B_MN) {
+            tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(b_dst + i * MN_ATOM_BYTES, &tmB, fb, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const int split = unit / num_tiles;
+      const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_src = sA + stage * A_STAGE_BYTES, b_src = sB + stage * C::B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? make_smem_desc_sw128(a_src + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
+                                        : make_smem_desc_sw128(a_src + k * (UMMA_K * 2), 16, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_src + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
+                                        : make_smem_desc_sw128(b_src + k * (UMMA_K * 2), 16, 1024);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);
+          if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * acc);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    const int e = warp - 4;
+    const int q = warp & 3;       // TMEM lane quarter this warp may read
+    const int half = e >> 2;      // which half of the BLOCK_N columns
+    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    int it = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+      const int split = unit / num_tiles, tile = unit - split * num_tiles;
+      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        if (c + 32 == COLS_PER_WARP) {
+          // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+        }
+        const int n0 = n_blk * BLOCK_N + half * COLS_PER_WARP + c;
+        if (!row_ok || n0 >= N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+        if (ep.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (n0 < ep.col_scale_ncols) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= ep.col_scale;
+        }
+        if (ep.out2) {
+          uint4* o = reinterpret_cast<uint4*>(ep.out2 + (long long)row * ep.ldo2 + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+        if (ep.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        } else if (ep.act == 2) {
+          const uint4* a4 = reinterpret_cast<const uint4*>(ep.aux + (long long)row * ep.ldaux + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 a = __ldg(a4 + j);
+            const float2 p0 = unpack_bf16x2(a.x), p1 = unpack_bf16x2(a.y), p2 = unpack_bf16x2(a.z),
+                         p3 = unpack_bf16x2(a.w);
+            v[8 * j] *= gelu_erf_grad(p0.x); v[8 * j + 1] *= gelu_erf_grad(p0.y);
+            v[8 * j + 2] *= gelu_erf_grad(p1.x); v[8 * j + 3] *= gelu_erf_grad(p1.y);
+            v[8 * j + 4] *= gelu_erf_grad(p2.x); v[8 * j + 5] *= gelu_erf_grad(p2.y);
+            v[8 * j + 6] *= gelu_erf_grad(p3.x); v[8 * j + 7] *= gelu_erf_grad(p3.y);
+          }
+        }
+        if (ep.residual) {
+          const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (long long)row * ep.ldr + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(r4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (ep.out_mode == 0) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (long long)row * ep.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        } else if (ep.out_mode == 1) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + n0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int splits,
+           const EpiParams& ep, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (!A_MN) rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K);
+  else       rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, BLOCK_K, 64);
+  if (rc) return rc;
+  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, BLOCK_N, BLOCK_K);
+  else       rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, BLOCK_K, 64);
+  if (rc) return rc;
+  const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M, num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  splits = max(1, min(splits, num_kb));
+  const int kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty splits
+  const int units = num_m_blocks * num_n_blocks * splits;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int grid = min(units, num_sms());
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, num_m_blocks, num_n_blocks, kb_per_split,
+                                                     splits, ep);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
+                   int splits, const EpiParams& ep, cudaStream_t stream) {
+  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && b_mn) return launch<BLOCK_N, false, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (a_mn && b_mn) return launch<BLOCK_N, true, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return launch<BLOCK_N, true, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
+
+}  // namespace
+
+}  // namespace egovlp
+
+using namespace egovlp;
+
+extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major,
+                                long long ldb, int M, int N, int K, const egovlp_gemm_epilogue* e, int split_k,
+                                void* stream) {
+  EGOVLP_CHECK_ARG(A && B && e && e->out, "gemm: null pointer");
+  EGOVLP_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: bad shape M=%d N=%d K=%d", M, N, K);
+  EGOVLP_CHECK_ARG(N % 32 == 0, "gemm: N=%d must be a multiple of 32", N);
+  EGOVLP_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16B TMA strides)");
+  EGOVLP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
+                   "gemm: operands must be 16B aligned");
+  EGOVLP_CHECK_ARG(e->out_mode >= 0 && e->out_mode <= 2 && e->act >= 0 && e->act <= 2, "gemm: bad epilogue mode");
+  EGOVLP_CHECK_ARG(split_k <= 1 || e->out_mode == 2, "gemm: split_k > 1 needs out_mode=2 (fp32 atomic accumulate)");
+  EGOVLP_CHECK_ARG(e->act != 2 || e->aux, "gemm: act=2 needs aux");
+  EGOVLP_CHECK_ARG(e->ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
+  EpiParams ep;
+  ep.bias = e->bias; ep.residual = e->residual; ep.aux = reinterpret_cast<const bf16*>(e->aux);
+  ep.out = e->out; ep.out2 = reinterpret_cast<bf16*>(e->out2);
+  ep.ldr = e->ldr; ep.ldaux = e->ldaux; ep.ldo = e->ldo; ep.ldo2 = e->ldo2;
+  ep.out_mode = e->out_mode; ep.act = e->act; ep.alpha = e->alpha;
+  ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (N % 256 == 0) return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+  return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+}

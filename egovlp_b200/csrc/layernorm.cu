@@ -1,0 +1,260 @@
+// LayerNorm forward / backward: one warp per row, float4 loads, warp-shuffle reductions, fp32 statistics.
+// HBM-bound: fwd reads 4D (+4D add) and writes 2D (+4D) bytes per row; bwd reads 8D (+adds), writes 4D (+2D).
+// Replaces nn.LayerNorm (model/video_transformer.py:146,156,159,228,253; DistilBERT LayerNorms) and its autograd.
+#include "common.cuh"
+#include "egovlp_b200.h"
+
+namespace egovlp {
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+template <int NV>  // NV float4 per lane: covers D <= NV*128
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ add,
+                     float* __restrict__ sum_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, int rows, int D, float eps) {
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)row * ldx;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      if (add) {
+        const float4 a = *reinterpret_cast<const float4*>(add + (long long)row * D + c);
+        v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+      }
+      if (sum_out) *reinterpret_cast<float4*>(sum_out + (long long)row * D + c) = v[i];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y16) *reinterpret_cast<uint2*>(y16 + (long long)row * D + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      if (y32) *reinterpret_cast<float4*>(y32 + (long long)row * D + c) = make_float4(o0, o1, o2, o3);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dx,
+                     bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
+  __shared__ float red[LN_WARPS][NV * 128 + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 pg[NV], pb[NV], g4[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb[i] = pg[i];
+    const int c = (i * 32 + lane) * 4;
+    g4[i] = (c < D) ? *reinterpret_cast<const float4*>(gamma + c) : pg[i];
+  }
+  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+    const float mu = mean[row], rs = rstd[row];
+    float4 dyv[NV], xh[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        dyv[i] = *reinterpret_cast<const float4*>(dy + (long long)row * lddy + c);
+        const float4 xv = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
+        xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        pg[i].x += dyv[i].x * xh[i].x; pg[i].y += dyv[i].y * xh[i].y; pg[i].z += dyv[i].z * xh[i].z; pg[i].w += dyv[i].w * xh[i].w;
+        pb[i].x += dyv[i].x; pb[i].y += dyv[i].y; pb[i].z += dyv[i].z; pb[i].w += dyv[i].w;
+        dyv[i].x *= g4[i].x; dyv[i].y *= g4[i].y; dyv[i].z *= g4[i].z; dyv[i].w *= g4[i].w;
+        s1 += dyv[i].x + dyv[i].y + dyv[i].z + dyv[i].w;
+        s2 += dyv[i].x * xh[i].x + dyv[i].y * xh[i].y + dyv[i].z * xh[i].z + dyv[i].w * xh[i].w;
+      }
+    }
+    const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        float4 o = make_float4(rs * (dyv[i].x - c1 - xh[i].x * c2), rs * (dyv[i].y - c1 - xh[i].y * c2),
+                               rs * (dyv[i].z - c1 - xh[i].z * c2), rs * (dyv[i].w - c1 - xh[i].w * c2));
+        const long long off = (long long)row * D + c;
+        if (add1) { const float4 a = *reinterpret_cast<const float4*>(add1 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (add2) { const float4 a = *reinterpret_cast<const float4*>(add2 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (dx) *reinterpret_cast<float4*>(dx + off) = o;
+        if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
+  }
+  if (!dgamma && !dbeta) return;
+  // block reduce the per-warp partial dgamma / dbeta, then one atomicAdd per column per block
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      const float4 p = pass == 0 ? pg[i] : pb[i];
+      red[warp][c] = p.x; red[warp][c + 1] = p.y; red[warp][c + 2] = p.z; red[warp][c + 3] = p.w;
+    }
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst) {
+      for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
+        atomicAdd(dst + c, s);
+      }
+    }
+  }
+}
+
+__global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(src + i);
+      *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    } else {
+      for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+    }
+  }
+}
+
+// out[n] += sum_m dy[m,n]; block = 32 x 8 threads, each block reduces a [rows_per_block, 32*VEC] slab.
+template <bool FP32>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ dy, long long ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (col < N) {
+    for (int r = r0 + ty; r < r1; r += 8) {
+      if (FP32) s += reinterpret_cast<const float*>(dy)[(long long)r * ld + col];
+      else s += __bfloat162float(reinterpret_cast<const bf16*>(dy)[(long long)r * ld + col]);
+    }
+  }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][tx];
+    atomicAdd(out + col, t);
+  }
+}
+
+template <int NV>
+int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_out, const float* gamma,
+                  const float* beta, void* y16, float* y32, float* mean, float* rstd, int rows, int D, float eps,
+                  cudaStream_t st) {
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(x, ldx, add, sum_out, gamma, beta,
+                                                          reinterpret_cast<bf16*>(y16), y32, mean, rstd, rows, D, eps);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+template <int NV>
+int launch_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+                  const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, void* dx16,
+                  float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 4);
+  layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
+                                                          reinterpret_cast<bf16*>(dx16), dgamma, dbeta, rows, D);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+}  // namespace
+}  // namespace egovlp
+
+using namespace egovlp;
+
+extern "C" int egovlp_layernorm_fwd(const float* x, long long ldx, const float* add, float* sum_out,
+                                    const float* gamma, const float* beta, void* y_bf16, float* y_f32, float* mean,
+                                    float* rstd, int rows, int D, float eps, void* stream) {
+  EGOVLP_CHECK_ARG(x && gamma && beta && (y_bf16 || y_f32), "layernorm_fwd: null pointer");
+  EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0, "layernorm_fwd: bad D=%d ldx=%lld", D, ldx);
+  if (rows == 0) return EGOVLP_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nv = (D + 127) / 128;
+#define LN_FWD_CASE(n) case n: return launch_ln_fwd<n>(x, ldx, add, sum_out, gamma, beta, y_bf16, y_f32, mean, rstd, rows, D, eps, st)
+  switch (nv) { LN_FWD_CASE(1); LN_FWD_CASE(2); LN_FWD_CASE(3); LN_FWD_CASE(4); LN_FWD_CASE(5); LN_FWD_CASE(6); LN_FWD_CASE(7); LN_FWD_CASE(8); }
+#undef LN_FWD_CASE
+  return EGOVLP_ERR_UNSUPPORTED;
+}
+
+extern "C" int egovlp_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx,
+                                    const float* gamma, const float* mean, const float* rstd, const float* add1,
+                                    const float* add2, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                                    int rows, int D, void* stream) {
+  EGOVLP_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_bf16), "layernorm_bwd: null pointer");
+  EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0, "layernorm_bwd: bad D=%d", D);
+  if (rows == 0) return EGOVLP_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int nv = (D + 127) / 128;
+#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, dx_bf16, dgamma, dbeta, rows, D, st)
+  switch (nv) { LN_BWD_CASE(1); LN_BWD_CASE(2); LN_BWD_CASE(3); LN_BWD_CASE(4); LN_BWD_CASE(5); LN_BWD_CASE(6); LN_BWD_CASE(7); LN_BWD_CASE(8); }
+#undef LN_BWD_CASE
+  return EGOVLP_ERR_UNSUPPORTED;
+}
+
+extern "C" int egovlp_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
+  EGOVLP_CHECK_ARG(src && dst_bf16 && n >= 0, "cast: bad args");
+  if (n == 0) return EGOVLP_OK;
+  EGOVLP_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0, "cast: alignment");
+  const long long blocks = (n / 4 + 255) / 256;
+  long long g = blocks < 1 ? 1 : blocks;
+  if (g > (long long)num_sms() * 16) g = (long long)num_sms() * 16;
+  const int grid = (int)g;
+  cast_f32_to_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<bf16*>(dst_bf16), n);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+extern "C" int egovlp_colsum_accum(const void* dy, int dy_is_fp32, long long ld, float* out, int M, int N,
+                                   void* stream) {
+  EGOVLP_CHECK_ARG(dy && out && M >= 0 && N > 0, "colsum: bad args");
+  if (M == 0) return EGOVLP_OK;
+  const int col_blocks = (N + 31) / 32;
+  int row_blocks = max(1, min((M + 63) / 64, (num_sms() * 8 + col_blocks - 1) / col_blocks));
+  const int rows_per_block = (M + row_blocks - 1) / row_blocks;
+  row_blocks = (M + rows_per_block - 1) / rows_per_block;
+  dim3 grid(col_blocks, row_blocks);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dy_is_fp32) colsum_kernel<true><<<grid, 256, 0, st>>>(dy, ld, out, M, N, rows_per_block);
+  else colsum_kernel<false><<<grid, 256, 0, st>>>(dy, ld, out, M, N, rows_per_block);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}

@@ -1,0 +1,142 @@
+"""Per-kernel parity on the GPU: every CUDA op against a plain torch fp32 restatement of the same op
+(called through the C-ABI via egovlp_b200.ops)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from egovlp_b200 import ops
+    return ops
+
+
+def rel_err(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
+
+
+def mk(shape, seed, scale=1.0, dtype=torch.bfloat16):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, generator=g, device="cuda") * scale).to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 768), (300, 768, 768), (1570, 2304, 768),
+                                   (130, 128, 64), (200, 64, 128), (1000, 3072, 768), (257, 768, 3072), (64, 32, 64)])
+def test_gemm_kmajor_bias(ops, M, N, K):
+    a, b = mk((M, K), 1), mk((N, K), 2, 0.05)
+    bias = mk((N,), 3, dtype=torch.float32)
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, b, out, bias=bias)
+    ref = a.float() @ b.float().t() + bias
+    assert rel_err(out, ref) < 4e-3
+    out32 = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out32, bias=bias)
+    assert rel_err(out32, ref) < 2e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 768, 2304), (1000, 3072, 768), (200, 64, 128)])
+def test_gemm_b_mn_major_dgrad(ops, M, N, K):
+    """dx = dy @ W with W stored [K, N] (n contiguous): the dgrad form."""
+    a, w = mk((M, K), 4), mk((K, N), 5, 0.05)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, w, out, b_mn=True)
+    assert rel_err(out, a.float() @ w.float()) < 2e-5
+
+
+@pytest.mark.parametrize("Mtok,N,Kin,split", [(512, 256, 256, 1), (1000, 768, 768, 4), (3137, 2304, 768, 7),
+                                              (777, 128, 64, 3)])
+def test_gemm_both_mn_major_wgrad(ops, Mtok, N, Kin, split):
+    """dW[N,Kin] += dy^T x : contraction over tokens, both operands token-major; split-K atomics."""
+    mt = (Mtok + 7) // 8 * 8
+    dy, x = mk((mt, N), 6), mk((mt, Kin), 7)
+    dy[Mtok:] = 0
+    base = mk((N, Kin), 8, dtype=torch.float32)
+    out = base.clone()
+    ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate=True, split_k=split)
+    ref = base + dy.float().t() @ x.float()
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_gemm_epilogues(ops):
+    M, N, K = 515, 768, 256
+    a, b = mk((M, K), 9), mk((N, K), 10, 0.06)
+    bias = mk((N,), 11, dtype=torch.float32)
+    res = mk((M, N), 12, dtype=torch.float32)
+    acc = a.float() @ b.float().t() + bias
+    # bias + residual -> fp32
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, bias=bias, residual=res)
+    assert rel_err(out, acc + res) < 2e-5
+    # bias + gelu, pre-activation saved
+    h = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    u = torch.empty_like(h)
+    ops.gemm(a, b, h, bias=bias, act=1, out2=u)
+    assert rel_err(u, acc) < 4e-3
+    assert rel_err(h, torch.nn.functional.gelu(acc)) < 4e-3
+    # multiply by gelu'(aux)
+    aux = mk((M, N), 13)
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, aux=aux, act=2)
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert rel_err(out, (a.float() @ b.float().t()) * x.grad) < 1e-4
+    # q-scale on the first 256 columns
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, bias=bias, col_scale=0.125, col_scale_ncols=256)
+    ref = acc.clone(); ref[:, :256] *= 0.125
+    assert rel_err(out, ref) < 2e-5
+
+
+def test_gemm_strided_views(ops):
+    """Operands / outputs that are column slices of wider buffers (ld > width)."""
+    M, N, K = 384, 256, 192
+    abuf, bbuf = mk((M, 3 * K), 14), mk((N, 2 * K), 15, 0.05)
+    obuf = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(abuf[:, K:2 * K], bbuf[:, K:], obuf[:, N:])
+    assert rel_err(obuf[:, N:], abuf[:, K:2 * K].float() @ bbuf[:, K:].float().t()) < 4e-3
+    assert torch.all(obuf[:, :N] == 0)
+
+
+@pytest.mark.parametrize("rows,D", [(1000, 768), (37, 64), (785 * 2, 768), (5, 128)])
+def test_layernorm_fwd_bwd(ops, rows, D):
+    x = mk((rows, D), 20, 2.0, torch.float32) + 0.3
+    g, b = mk((D,), 21, dtype=torch.float32) * 0.1 + 1, mk((D,), 22, dtype=torch.float32) * 0.1
+    y16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    y32 = torch.empty(rows, D, device="cuda", dtype=torch.float32)
+    mean, rstd = torch.empty(rows, device="cuda"), torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, g, b, 1e-6, y16=y16, y32=y32, mean=mean, rstd=rstd)
+    xr = x.clone().requires_grad_(True)
+    gr, br = g.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
+    assert rel_err(y32, ref) < 1e-5 and rel_err(y16, ref) < 4e-3
+    dy = mk((rows, D), 23, dtype=torch.float32)
+    a1, a2 = mk((rows, D), 24, dtype=torch.float32), mk((rows, D), 25, dtype=torch.float32)
+    ref.backward(dy)
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    dg, db = torch.zeros(D, device="cuda"), torch.zeros(D, device="cuda")
+    ops.layernorm_bwd(dy, x, g, mean, rstd, add1=a1, add2=a2, dx=dx, dx16=dx16, dgamma=dg, dbeta=db)
+    assert rel_err(dx, xr.grad + a1 + a2) < 1e-5
+    assert rel_err(dx16, xr.grad + a1 + a2) < 4e-3
+    assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+
+
+def test_layernorm_fused_add(ops):
+    rows, D = 300, 768
+    x, a = mk((rows, D), 30, dtype=torch.float32), mk((rows, D), 31, dtype=torch.float32)
+    g, b = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
+    s = torch.empty_like(x); y = torch.empty_like(x)
+    ops.layernorm_fwd(x, g, b, 1e-12, add=a, sum_out=s, y32=y)
+    assert torch.equal(s, x + a)
+    assert rel_err(y, torch.nn.functional.layer_norm(x + a, (D,), g, b, 1e-12)) < 1e-5
+
+
+def test_cast_and_colsum(ops):
+    w = mk((1000, 771), 40, dtype=torch.float32)
+    assert torch.equal(ops.cast_bf16(w), w.to(torch.bfloat16))
+    for dt in (torch.float32, torch.bfloat16):
+        dy = mk((3137, 768), 41, dtype=dt)
+        out = torch.ones(768, device="cuda")
+        ops.colsum_accum(dy, out)
+        assert rel_err(out, 1 + dy.float().sum(0)) < 1e-5
