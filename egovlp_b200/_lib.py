@@ -27,6 +27,7 @@ def lib():
                               "(there is no CPU / PyTorch fallback for the hot path)")
         _lib = C.CDLL(LIB_PATH)
         _lib.egovlp_last_error.restype = C.c_char_p
+        _lib.egovlp_divided_attn_workspace_floats.restype = C.c_longlong
     return _lib
 
 

@@ -1,0 +1,668 @@
+// Divided space-time attention of the video tower, forward and backward, with the reference's CLS semantics.
+//
+// Replaces VarAttention.forward's attention core (model/video_transformer.py:104-133: the head split, q scaling,
+// CLS splice, the two einops rearranges, the CLS k/v repeat + cat, attn() = softmax(q k^T) v, and the merges)
+// and its autograd.  Input is the QKV GEMM's output qkv[B*S, 3*D] (bf16, q already scaled), output is
+// out[B*S, D] (bf16) ready for the proj GEMM -- no rearranged copy, no materialised probabilities.
+//
+// One CTA per group: (b, head, frame) for space, (b, head, block of PG patches) for time.  The group's
+// queries/keys/values are gathered straight from qkv by ONE 5-D TMA box each (128B-swizzled rows of one head),
+// the CLS token's q/k/v row is appended as row NP.  A group's rows carry a group id (time: the patch, space: 0);
+// query r may attend key c iff  gid[c] == gid[r]  or c is the CLS key; the CLS query attends every patch key
+// of the CTA plus the CLS key in the first group only, and its per-group (max, sum, acc) partials are merged by
+// a tiny second kernel -- so the CLS-over-all-S row (:112) costs no extra pass over K/V.
+// Math: bf16 mma.sync m16n8k16 with fp32 accumulation + fp32 online softmax (exp2).  This op is HBM-bound on
+// B200 (<= 98 FLOP/B), so the legacy tensor path is sufficient to sit on the HBM roofline;
+// the tcgen05 pipeline is reserved for the GEMMs that carry 96% of the FLOPs.
+#include "common.cuh"
+#include "egovlp_b200.h"
+
+namespace egovlp {
+namespace {
+
+constexpr int HD = 64;            // head dim
+constexpr int ROW_BYTES = 128;    // one head-row of bf16
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct Geom {
+  int B, H, T, N, S, D;     // D = H * 64
+  int mode;                 // 0 time, 1 space
+  int PG;                   // patches per group (time)
+  int G;                    // groups per (b, h)
+  int NP;                   // patch rows per group (space: N, time: PG*T)
+  int NPAD;                 // NP + 1 rounded up to 16
+  int gsize;                // rows per group id (space: N, time: T)
+};
+
+__device__ __forceinline__ uint32_t sw_addr(uint32_t base, int row, int chunk) {
+  return base + row * ROW_BYTES + ((chunk ^ (row & 7)) << 4);
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A-operand fragment (16 rows x 16 k) of a swizzled [rows x 64] tile: rows r0.., k-step kk
+__device__ __forceinline__ void load_a_frag(uint32_t tile, int r0, int kk, int lane, uint32_t (&f)[4]) {
+  ldsm_x4(sw_addr(tile, r0 + (lane & 7) + ((lane >> 3) & 1) * 8, kk * 2 + (lane >> 4)), f);
+}
+// B-operand fragments for two 8-wide n-tiles (n = rows n0..n0+15 of the tile, k = its 64 columns), k-step kk
+__device__ __forceinline__ void load_b_frag_nk(uint32_t tile, int n0, int kk, int lane, uint32_t (&f)[4]) {
+  ldsm_x4(sw_addr(tile, n0 + (lane & 7) + (lane >> 4) * 8, kk * 2 + ((lane >> 3) & 1)), f);
+}
+// B-operand fragments with k = rows k0..k0+15 of the tile, n = columns dp*16..dp*16+15 (two n-tiles), transposed load
+__device__ __forceinline__ void load_b_frag_kn(uint32_t tile, int k0, int dp, int lane, uint32_t (&f)[4]) {
+  ldsm_x4_t(sw_addr(tile, k0 + (lane & 7) + ((lane >> 3) & 1) * 8, dp * 2 + (lane >> 4)), f);
+}
+
+// token (0..S-1) held by smem row r of group g, or -1 for padding / out-of-range patches
+__device__ __forceinline__ int row_token(const Geom& G, int g, int r) {
+  if (r == G.NP) return 0;
+  if (r > G.NP) return -1;
+  if (G.mode == 1) return 1 + g * G.N + r;
+  const int j = r / G.T, f = r - j * G.T, n = g * G.PG + j;
+  return n < G.N ? 1 + f * G.N + n : -1;
+}
+
+struct Smem {
+  uint32_t q, k, v, dout;  // tile base addresses (shared space)
+  short* gid;              // [NPAD] group id per row; -2 = CLS, -1 = invalid
+  float* lse;              // [NPAD]  (backward)
+  float* delta;            // [NPAD]  (backward)
+  uint32_t stage;          // per-warp staging [warps][16 x 128B]
+  uint32_t bar;
+};
+
+__device__ __forceinline__ bool pair_valid(int gq, int gk, bool first_group) {
+  if (gq >= 0) return gk == gq || gk == -2;
+  if (gq == -2) return gk >= 0 || (gk == -2 && first_group);
+  return false;
+}
+
+// Range of "other side" rows a 16-row tile starting at r0 can interact with: [lo, hi) plus the CLS row NP.
+__device__ __forceinline__ void tile_window(const Geom& G, int r0, int& lo, int& hi) {
+  if (r0 <= G.NP && G.NP < r0 + 16) { lo = 0; hi = G.NP; return; }   // tile holds the CLS row: everything
+  if (r0 > G.NP) { lo = 0; hi = 0; return; }
+  lo = (r0 / G.gsize) * G.gsize;
+  hi = min(G.NP, ((r0 + 15) / G.gsize + 1) * G.gsize);
+}
+__device__ __forceinline__ bool span_active(const Geom& G, int lo, int hi, int c0, int width) {
+  return (c0 < hi && c0 + width > lo) || (c0 <= G.NP && G.NP < c0 + width);
+}
+
+// Stage a 16 x 64 fp32 fragment tile (mma C layout, 8 n-tiles) as bf16 into the warp's staging rows, then write
+// each valid row as one 128-byte line to dst[(b*S + token) * ld + col0 ...].
+__device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float s0, float s1, uint32_t stage,
+                                                uint8_t* stage_gen, bf16* dst, long long ld, int col0, const Geom& G,
+                                                int b, int g, int r0, int lane, bool skip_cls) {
+  const int gq = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t lo = pack_bf16x2(acc[j][0] * s0, acc[j][1] * s0), hi = pack_bf16x2(acc[j][2] * s1, acc[j][3] * s1);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(stage, gq, j) + t * 4), "r"(lo));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(sw_addr(stage, gq + 8, j) + t * 4), "r"(hi));
+  }
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int rr = p * 4 + (lane >> 3), c = lane & 7;
+    const int tok = row_token(G, g, r0 + rr);
+    if (tok > 0 || (tok == 0 && !skip_cls)) {
+      const uint4 v = *reinterpret_cast<const uint4*>(stage_gen + (sw_addr(stage, rr, c) - stage));
+      *reinterpret_cast<uint4*>(dst + ((long long)b * G.S + tok) * ld + col0 + c * 8) = v;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int& g) {
+  g = blockIdx.x % G.G;
+  const int bh = blockIdx.x / G.G;
+  h = bh % G.H;
+  b = bh / G.H;
+}
+
+// Shared prologue: carve smem, gather the group's tiles (TMA) + CLS rows (manual), build the gid table.
+template <bool BWD>
+__device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_qkv, const CUtensorMap* tm_do,
+                                           const bf16* qkv, const bf16* dout, int b, int h, int g, uint8_t* smem_gen,
+                                           uint32_t smem_base, Smem& sm, int nwarps) {
+  const int tile_bytes = G.NPAD * ROW_BYTES;
+  sm.q = smem_base;
+  sm.k = sm.q + tile_bytes;
+  sm.v = sm.k + tile_bytes;
+  sm.dout = sm.v + tile_bytes;
+  uint32_t off = (BWD ? 4 : 3) * tile_bytes;
+  sm.stage = smem_base + off;
+  off += nwarps * 16 * ROW_BYTES;
+  sm.lse = reinterpret_cast<float*>(smem_gen + off);
+  off += G.NPAD * 4;
+  sm.delta = reinterpret_cast<float*>(smem_gen + off);
+  off += G.NPAD * 4;
+  sm.gid = reinterpret_cast<short*>(smem_gen + off);
+  off += ((G.NPAD * 2 + 15) / 16) * 16;
+  sm.bar = smem_base + off;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(sm.bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int ntiles = BWD ? 4 : 3;
+  if (tid == 0) {
+    const int rows = (G.mode == 1) ? G.N : G.T * G.PG;
+    mbar_expect_tx(sm.bar, (uint32_t)(ntiles * rows * ROW_BYTES));
+    const int f0 = (G.mode == 1) ? g : 0, n0 = (G.mode == 1) ? 0 : g * G.PG;
+    tma_load_5d(sm.q, tm_qkv, sm.bar, 0, f0, n0, 0 * G.H + h, b);
+    tma_load_5d(sm.k, tm_qkv, sm.bar, 0, f0, n0, 1 * G.H + h, b);
+    tma_load_5d(sm.v, tm_qkv, sm.bar, 0, f0, n0, 2 * G.H + h, b);
+    if (BWD) tma_load_5d(sm.dout, tm_do, sm.bar, 0, f0, n0, h, b);
+  }
+  // CLS rows (row NP) + zero padding rows NP+1 .. NPAD-1, 16B chunks
+  const int pad_rows = G.NPAD - G.NP;   // >= 1
+  for (int i = tid; i < ntiles * pad_rows * 8; i += blockDim.x) {
+    const int c = i & 7, rr = (i >> 3) % pad_rows, which = (i >> 3) / pad_rows;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (rr == 0) {
+      const bf16* src = (which < 3) ? qkv + (long long)b * G.S * 3 * G.D + which * G.D + h * HD
+                                    : dout + (long long)b * G.S * G.D + h * HD;
+      val = *reinterpret_cast<const uint4*>(src + c * 8);
+    }
+    *reinterpret_cast<uint4*>(smem_gen + (sw_addr(sm.q + which * tile_bytes, G.NP + rr, c) - smem_base)) = val;
+  }
+  for (int r = tid; r < G.NPAD; r += blockDim.x) {
+    short gid = -1;
+    if (r == G.NP) gid = -2;
+    else if (r < G.NP && row_token(G, g, r) > 0) gid = (short)(r / G.gsize);
+    sm.gid[r] = gid;
+  }
+  __syncthreads();
+  mbar_wait(sm.bar, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+divided_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __restrict__ qkv,
+                        bf16* __restrict__ out, float* __restrict__ lse_out, float* __restrict__ cls_part, Geom G) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  int b, h, g;
+  decode_block(G, b, h, g);
+  Smem sm;
+  load_group<false>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const bool first_group = (g == 0);
+  const int NT = G.NPAD / 8;
+  const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
+  uint8_t* stage_gen = smem_gen + (stage - smem_base);
+
+  for (int rt = warp; rt * 16 <= G.NP; rt += NWARPS) {
+    const int r0 = rt * 16;
+    int lo, hi;
+    tile_window(G, r0, lo, hi);
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) load_a_frag(sm.q, r0, kk, lane, qf[kk]);
+    const int gid0 = sm.gid[r0 + gq], gid1 = sm.gid[r0 + gq + 8];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+
+    for (int c0 = 0; c0 < NT; c0 += 8) {     // chunk of 8 n-tiles = 64 keys
+      if (!span_active(G, lo, hi, c0 * 8, 64)) continue;
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int n0 = (c0 + 2 * p) * 8;
+        if (c0 + 2 * p < NT && span_active(G, lo, hi, n0, 16)) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t bf[4];
+            load_b_frag_nk(sm.k, n0, kk, lane, bf);
+            mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
+            mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
+          }
+        }
+      }
+      // mask
+      float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = (c0 + j) * 8 + 2 * t;
+        const bool inb = (c0 + j) < NT;
+        const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
+        s[j][0] = pair_valid(gid0, k0, first_group) ? s[j][0] : -INFINITY;
+        s[j][1] = pair_valid(gid0, k1, first_group) ? s[j][1] : -INFINITY;
+        s[j][2] = pair_valid(gid1, k0, first_group) ? s[j][2] : -INFINITY;
+        s[j][3] = pair_valid(gid1, k1, first_group) ? s[j][3] : -INFINITY;
+        cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+        cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+      }
+      cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+      cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+      const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+      const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0, ms1 = (mn1 == -INFINITY) ? 0.f : mn1;
+      const float a0 = exp2f((m0 - ms0) * LOG2E), a1 = exp2f((m1 - ms1) * LOG2E);   // m = -inf -> 0
+      m0 = mn0; m1 = mn1;
+      l0 *= a0; l1 *= a1;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f((s[j][0] - ms0) * LOG2E), p1 = exp2f((s[j][1] - ms0) * LOG2E);
+        const float p2 = exp2f((s[j][2] - ms1) * LOG2E), p3 = exp2f((s[j][3] - ms1) * LOG2E);
+        l0 += p0 + p1; l1 += p2 + p3;
+        pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int k0 = (c0 + 2 * kk) * 8;
+        if (c0 + 2 * kk < NT && span_active(G, lo, hi, k0, 16)) {
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t bf[4];
+            load_b_frag_kn(sm.v, k0, dp, lane, bf);
+            mma_bf16(o[2 * dp], pf[kk], bf[0], bf[1]);
+            mma_bf16(o[2 * dp + 1], pf[kk], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // CLS query row: un-normalised partial for the merge kernel
+    {
+      const int rc = G.NP - r0;   // local index of the CLS row in this tile, if any
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dst = cls_part + (((long long)(b * G.H + h)) * G.G + g) * 66;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[j * 8 + 2 * t] = hi_half ? o[j][2] : o[j][0];
+          dst[j * 8 + 2 * t + 1] = hi_half ? o[j][3] : o[j][1];
+        }
+        if (t == 0) { dst[64] = hi_half ? m1 : m0; dst[65] = hi_half ? l1 : l0; }
+      }
+    }
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    if (t == 0) {
+      const int tok0 = row_token(G, g, r0 + gq), tok1 = row_token(G, g, r0 + gq + 8);
+      if (tok0 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok0] = m0 + logf(l0);
+      if (tok1 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok1] = m1 + logf(l1);
+    }
+    store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
+  }
+}
+
+// merge the per-group partials of the CLS query: one warp per (b, h)
+__global__ void cls_merge_kernel(const float* __restrict__ part, bf16* __restrict__ out, float* __restrict__ lse,
+                                 int BH, int H, int Gn, int S, int D) {
+  const int bh = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (bh >= BH) return;
+  const int lane = threadIdx.x & 31;
+  const float* p = part + (long long)bh * Gn * 66;
+  float M = -INFINITY;
+  for (int g = 0; g < Gn; ++g) M = fmaxf(M, p[g * 66 + 64]);
+  float L = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int g = 0; g < Gn; ++g) {
+    const float mg = p[g * 66 + 64];
+    const float w = (mg == -INFINITY) ? 0.f : exp2f((mg - M) * LOG2E);
+    L += p[g * 66 + 65] * w;
+    o0 += p[g * 66 + 2 * lane] * w;
+    o1 += p[g * 66 + 2 * lane + 1] * w;
+  }
+  const int b = bh / H, h = bh % H;
+  const float inv = 1.f / L;
+  *reinterpret_cast<uint32_t*>(out + (long long)b * S * D + h * HD + 2 * lane) = pack_bf16x2(o0 * inv, o1 * inv);
+  if (lane == 0) lse[(long long)bh * S] = M + logf(L);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+template <int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                        const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                        const float* __restrict__ lse_in, bf16* __restrict__ dqkv, float* __restrict__ dcls,
+                        float q_scale, Geom G) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  int b, h, g;
+  decode_block(G, b, h, g);
+  Smem sm;
+  load_group<true>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const bool first_group = (g == 0);
+  const int NT = G.NPAD / 8;
+  const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
+  uint8_t* stage_gen = smem_gen + (stage - smem_base);
+
+  // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row
+  for (int r = warp * 4 + (lane >> 3); r < G.NPAD; r += NWARPS * 4) {
+    const int tok = row_token(G, g, r), c = lane & 7;
+    float d = 0.f;
+    if (tok >= 0) {
+      const uint4 ov = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + c * 8);
+      const uint4 dv = *reinterpret_cast<const uint4*>(smem_gen + (sw_addr(sm.dout, r, c) - smem_base));
+      const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack_bf16x2(ou[i]), bb = unpack_bf16x2(du[i]);
+        d += a.x * bb.x + a.y * bb.y;
+      }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (c == 0) {
+      sm.delta[r] = d;
+      sm.lse[r] = tok >= 0 ? lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // phase 1: per 16 query rows -> dQ
+  for (int rt = warp; rt * 16 <= G.NP; rt += NWARPS) {
+    const int r0 = rt * 16;
+    int lo, hi;
+    tile_window(G, r0, lo, hi);
+    uint32_t qf[4][4], df[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { load_a_frag(sm.q, r0, kk, lane, qf[kk]); load_a_frag(sm.dout, r0, kk, lane, df[kk]); }
+    const int gid0 = sm.gid[r0 + gq], gid1 = sm.gid[r0 + gq + 8];
+    const float ls0 = sm.lse[r0 + gq], ls1 = sm.lse[r0 + gq + 8], de0 = sm.delta[r0 + gq], de1 = sm.delta[r0 + gq + 8];
+    float dq[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
+    for (int c0 = 0; c0 < NT; c0 += 4) {     // chunk of 4 n-tiles = 32 keys
+      if (!span_active(G, lo, hi, c0 * 8, 32)) continue;
+      float s[4][4], dp[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int n0 = (c0 + 2 * p) * 8;
+        if (c0 + 2 * p < NT && span_active(G, lo, hi, n0, 16)) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t bf[4];
+            load_b_frag_nk(sm.k, n0, kk, lane, bf);
+            mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
+            mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
+            load_b_frag_nk(sm.v, n0, kk, lane, bf);
+            mma_bf16(dp[2 * p], df[kk], bf[0], bf[1]);
+            mma_bf16(dp[2 * p + 1], df[kk], bf[2], bf[3]);
+          }
+        }
+      }
+      uint32_t dsf[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = (c0 + j) * 8 + 2 * t;
+        const bool inb = (c0 + j) < NT;
+        const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
+        const float p0 = pair_valid(gid0, k0, first_group) ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
+        const float p1 = pair_valid(gid0, k1, first_group) ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
+        const float p2 = pair_valid(gid1, k0, first_group) ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
+        const float p3 = pair_valid(gid1, k1, first_group) ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
+        dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
+        dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k0 = (c0 + 2 * kk) * 8;
+        if (c0 + 2 * kk < NT && span_active(G, lo, hi, k0, 16)) {
+#pragma unroll
+          for (int dpi = 0; dpi < 4; ++dpi) {
+            uint32_t bf[4];
+            load_b_frag_kn(sm.k, k0, dpi, lane, bf);
+            mma_bf16(dq[2 * dpi], dsf[kk], bf[0], bf[1]);
+            mma_bf16(dq[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    // CLS query row -> fp32 atomics (summed over groups); patch rows -> dqkv q-columns (scaled back)
+    {
+      const int rc = G.NP - r0;
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dst = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(dst + j * 8 + 2 * t, hi_half ? dq[j][2] : dq[j][0]);
+          atomicAdd(dst + j * 8 + 2 * t + 1, hi_half ? dq[j][3] : dq[j][1]);
+        }
+      }
+    }
+    store_rows_bf16(dq, q_scale, q_scale, stage, stage_gen, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane, true);
+  }
+
+  // phase 2: per 16 keys -> dK, dV
+  for (int kt = warp; kt * 16 <= G.NP; kt += NWARPS) {
+    const int k0r = kt * 16;
+    int lo, hi;
+    tile_window(G, k0r, lo, hi);
+    uint32_t kf[4][4], vf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) { load_a_frag(sm.k, k0r, kk, lane, kf[kk]); load_a_frag(sm.v, k0r, kk, lane, vf[kk]); }
+    const int gid0 = sm.gid[k0r + gq], gid1 = sm.gid[k0r + gq + 8];
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
+    for (int c0 = 0; c0 < NT; c0 += 4) {     // chunk of 4 n-tiles = 32 queries
+      if (!span_active(G, lo, hi, c0 * 8, 32)) continue;
+      float st[4][4], dpt[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f; }
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int n0 = (c0 + 2 * p) * 8;
+        if (c0 + 2 * p < NT && span_active(G, lo, hi, n0, 16)) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            uint32_t bf[4];
+            load_b_frag_nk(sm.q, n0, kk, lane, bf);
+            mma_bf16(st[2 * p], kf[kk], bf[0], bf[1]);
+            mma_bf16(st[2 * p + 1], kf[kk], bf[2], bf[3]);
+            load_b_frag_nk(sm.dout, n0, kk, lane, bf);
+            mma_bf16(dpt[2 * p], vf[kk], bf[0], bf[1]);
+            mma_bf16(dpt[2 * p + 1], vf[kk], bf[2], bf[3]);
+          }
+        }
+      }
+      uint32_t pf[2][4], dsf[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = (c0 + j) * 8 + 2 * t;       // query index
+        const bool inb = (c0 + j) < NT;
+        const int q0 = inb ? sm.gid[col] : -1, q1 = inb ? sm.gid[col + 1] : -1;
+        const float lq0 = inb ? sm.lse[col] : 0.f, lq1 = inb ? sm.lse[col + 1] : 0.f;
+        const float dq0 = inb ? sm.delta[col] : 0.f, dq1 = inb ? sm.delta[col + 1] : 0.f;
+        const float p0 = pair_valid(q0, gid0, first_group) ? exp2f(st[j][0] * LOG2E - lq0) : 0.f;
+        const float p1 = pair_valid(q1, gid0, first_group) ? exp2f(st[j][1] * LOG2E - lq1) : 0.f;
+        const float p2 = pair_valid(q0, gid1, first_group) ? exp2f(st[j][2] * LOG2E - lq0) : 0.f;
+        const float p3 = pair_valid(q1, gid1, first_group) ? exp2f(st[j][3] * LOG2E - lq1) : 0.f;
+        pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq0), p1 * (dpt[j][1] - dq1));
+        dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dpt[j][2] - dq0), p3 * (dpt[j][3] - dq1));
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const int q0r = (c0 + 2 * kk) * 8;
+        if (c0 + 2 * kk < NT && span_active(G, lo, hi, q0r, 16)) {
+#pragma unroll
+          for (int dpi = 0; dpi < 4; ++dpi) {
+            uint32_t bf[4];
+            load_b_frag_kn(sm.dout, q0r, dpi, lane, bf);
+            mma_bf16(dv[2 * dpi], pf[kk], bf[0], bf[1]);
+            mma_bf16(dv[2 * dpi + 1], pf[kk], bf[2], bf[3]);
+            load_b_frag_kn(sm.q, q0r, dpi, lane, bf);
+            mma_bf16(dk[2 * dpi], dsf[kk], bf[0], bf[1]);
+            mma_bf16(dk[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    {
+      const int rc = G.NP - k0r;
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dstk = dcls + ((long long)(b * G.H + h) * 3 + 1) * HD;
+        float* dstv = dcls + ((long long)(b * G.H + h) * 3 + 2) * HD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(dstk + j * 8 + 2 * t, hi_half ? dk[j][2] : dk[j][0]);
+          atomicAdd(dstk + j * 8 + 2 * t + 1, hi_half ? dk[j][3] : dk[j][1]);
+          atomicAdd(dstv + j * 8 + 2 * t, hi_half ? dv[j][2] : dv[j][0]);
+          atomicAdd(dstv + j * 8 + 2 * t + 1, hi_half ? dv[j][3] : dv[j][1]);
+        }
+      }
+    }
+    store_rows_bf16(dk, 1.f, 1.f, stage, stage_gen, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane, true);
+    store_rows_bf16(dv, 1.f, 1.f, stage, stage_gen, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane, true);
+  }
+}
+
+// dqkv[b, 0, which*D + h*64 + d] = bf16(dcls[b,h,which,d] * (which == 0 ? q_scale : 1))
+__global__ void cls_grad_finalize_kernel(const float* __restrict__ dcls, bf16* __restrict__ dqkv, int B, int H, int S,
+                                         int D, float q_scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H * 3 * HD) return;
+  const int d = i % HD, which = (i / HD) % 3, h = (i / (3 * HD)) % H, b = i / (3 * HD * H);
+  const float v = dcls[i] * (which == 0 ? q_scale : 1.f);
+  dqkv[(long long)b * S * 3 * D + which * D + h * HD + d] = __float2bfloat16(v);
+}
+
+int make_geom(Geom& G, int B, int T, int N, int H, int mode) {
+  G.B = B; G.H = H; G.T = T; G.N = N; G.S = 1 + T * N; G.D = H * HD; G.mode = mode;
+  if (mode == 1) {
+    G.PG = N; G.G = T; G.NP = N; G.gsize = N;
+  } else {
+    G.PG = min(N, 127 / T);
+    if (G.PG < 1) return EGOVLP_ERR_UNSUPPORTED;
+    G.G = (N + G.PG - 1) / G.PG; G.NP = G.PG * T; G.gsize = T;
+  }
+  G.NPAD = (G.NP + 1 + 15) / 16 * 16;
+  if (G.NPAD > 256 || (mode == 1 ? N : max(T, G.PG)) > 256) return EGOVLP_ERR_UNSUPPORTED;
+  return EGOVLP_OK;
+}
+
+// 5-D gather map over a [B*S, ncolblk*64] bf16 matrix: dims (d, f, n, colblk, b), CLS row skipped via the base.
+int make_group_tmap(CUtensorMap* tm, const void* base, const Geom& G, int ncolblk) {
+  const uint64_t W = (uint64_t)ncolblk * HD;
+  const uint64_t dims[5] = {HD, (uint64_t)G.T, (uint64_t)G.N, (uint64_t)ncolblk, (uint64_t)G.B};
+  const uint64_t strides[5] = {1, (uint64_t)G.N * W, W, HD, (uint64_t)G.S * W};
+  const uint32_t box[5] = {HD, (uint32_t)(G.mode == 1 ? 1 : G.T), (uint32_t)(G.mode == 1 ? G.N : G.PG), 1, 1};
+  return make_tmap_nd_bf16(tm, reinterpret_cast<const bf16*>(base) + W, 5, dims, strides, box, true);
+}
+
+size_t attn_smem_bytes(const Geom& G, bool bwd, int nwarps) {
+  return (size_t)(bwd ? 4 : 3) * G.NPAD * ROW_BYTES + nwarps * 16 * ROW_BYTES + 2 * G.NPAD * 4 +
+         ((G.NPAD * 2 + 15) / 16) * 16 + 16 + 1024;
+}
+
+
+}  // namespace
+}  // namespace egovlp
+
+using namespace egovlp;
+
+extern "C" long long egovlp_divided_attn_workspace_floats(int B, int T, int N, int H, int mode) {
+  Geom G;
+  if (make_geom(G, B, T, N, H, mode)) return -1;
+  return (long long)B * H * G.G * 66;
+}
+
+extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N,
+                                       int H, int mode, void* stream) {
+  EGOVLP_CHECK_ARG(qkv && out && lse && cls_part, "divided_attn_fwd: null pointer");
+  EGOVLP_CHECK_ARG(B > 0 && T > 0 && N > 0 && H > 0 && (mode == 0 || mode == 1), "divided_attn_fwd: bad shape");
+  Geom G;
+  if (make_geom(G, B, T, N, H, mode)) { set_last_error("divided_attn: unsupported geometry T=%d N=%d", T, N); return EGOVLP_ERR_UNSUPPORTED; }
+  CUtensorMap tm;
+  int rc = make_group_tmap(&tm, qkv, G, 3 * H);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (G.NPAD > 128) {   // space, 196 patches: 13 row tiles over 7 warps, 2 CTAs / SM
+    constexpr int W = 7;
+    const size_t smem = attn_smem_bytes(G, false, W);
+    auto kern = divided_attn_fwd_kernel<W, 2>;
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * H * G.G, W * 32, smem, st>>>(tm, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse,
+                                           cls_part, G);
+  } else {              // time (<= 8 row tiles) and small test geometries
+    constexpr int W = 4;
+    const size_t smem = attn_smem_bytes(G, false, W);
+    auto kern = divided_attn_fwd_kernel<W, 3>;
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * H * G.G, W * 32, smem, st>>>(tm, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse,
+                                           cls_part, G);
+  }
+  EGOVLP_CHECK_LAUNCH();
+  const int BH = B * H;
+  cls_merge_kernel<<<(BH + 3) / 4, 128, 0, st>>>(cls_part, reinterpret_cast<bf16*>(out), lse, BH, H, G.G, G.S, G.D);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+extern "C" int egovlp_divided_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse,
+                                       void* dqkv, float* dcls_ws, int B, int T, int N, int H, int mode,
+                                       float q_scale, void* stream) {
+  EGOVLP_CHECK_ARG(qkv && out && dout && lse && dqkv && dcls_ws, "divided_attn_bwd: null pointer");
+  EGOVLP_CHECK_ARG(B > 0 && T > 0 && N > 0 && H > 0 && (mode == 0 || mode == 1), "divided_attn_bwd: bad shape");
+  Geom G;
+  if (make_geom(G, B, T, N, H, mode)) { set_last_error("divided_attn: unsupported geometry T=%d N=%d", T, N); return EGOVLP_ERR_UNSUPPORTED; }
+  CUtensorMap tmq, tmd;
+  int rc = make_group_tmap(&tmq, qkv, G, 3 * H);
+  if (rc) return rc;
+  rc = make_group_tmap(&tmd, dout, G, H);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  EGOVLP_CHECK_CUDA(cudaMemsetAsync(dcls_ws, 0, (size_t)B * H * 3 * HD * sizeof(float), st));
+  if (G.NPAD > 128) {   // space: 13 row tiles over 7 warps, 1 CTA / SM (4 tiles of 26 KB), up to 255 registers
+    constexpr int W = 7;
+    const size_t smem = attn_smem_bytes(G, true, W);
+    auto kern = divided_attn_bwd_kernel<W, 1>;
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * H * G.G, W * 32, smem, st>>>(tmq, tmd, reinterpret_cast<const bf16*>(qkv),
+                                           reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), lse,
+                                           reinterpret_cast<bf16*>(dqkv), dcls_ws, q_scale, G);
+  } else {
+    constexpr int W = 4;
+    const size_t smem = attn_smem_bytes(G, true, W);
+    auto kern = divided_attn_bwd_kernel<W, 3>;
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B * H * G.G, W * 32, smem, st>>>(tmq, tmd, reinterpret_cast<const bf16*>(qkv),
+                                           reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), lse,
+                                           reinterpret_cast<bf16*>(dqkv), dcls_ws, q_scale, G);
+  }
+  EGOVLP_CHECK_LAUNCH();
+  const int n = B * H * 3 * HD;
+  cls_grad_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(dcls_ws, reinterpret_cast<bf16*>(dqkv), B, H, G.S, G.D, q_scale);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}

@@ -4,7 +4,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import GemmEpilogue, call
+from ._lib import GemmEpilogue, call, lib
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -98,3 +98,28 @@ def colsum_accum(dy, out):
     assert dy.dim() == 2 and dy.stride(1) == 1 and out.dtype == F32 and out.numel() == dy.shape[1]
     call("egovlp_colsum_accum", _ptr(dy), int(dy.dtype == F32), C.c_longlong(dy.stride(0)), _ptr(out), dy.shape[0],
          dy.shape[1], _stream())
+
+
+def divided_attn_fwd(qkv, B, T, N, H, mode):
+    """qkv bf16 [B*S, 3*64*H] (q pre-scaled) -> (out bf16 [B*S, D], lse fp32 [B, H, S]).  mode: 0 time, 1 space."""
+    _chk(qkv, BF16, "qkv")
+    S, D = 1 + T * N, 64 * H
+    assert qkv.is_contiguous() and qkv.shape == (B * S, 3 * D)
+    out = torch.empty(B * S, D, dtype=BF16, device=qkv.device)
+    lse = torch.empty(B, H, S, dtype=F32, device=qkv.device)
+    n_ws = lib().egovlp_divided_attn_workspace_floats(B, T, N, H, mode)
+    assert n_ws > 0, "unsupported attention geometry"
+    ws = torch.empty(n_ws, dtype=F32, device=qkv.device)
+    call("egovlp_divided_attn_fwd", _ptr(qkv), _ptr(out), _ptr(lse), _ptr(ws), B, T, N, H, mode, _stream())
+    return out, lse
+
+
+def divided_attn_bwd(qkv, out, dout, lse, B, T, N, H, mode, q_scale, dqkv=None):
+    _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out"); _chk(dout, BF16, "dout"); _chk(lse, F32, "lse")
+    assert qkv.is_contiguous() and out.is_contiguous() and dout.is_contiguous() and lse.is_contiguous()
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B * H * 3 * 64, dtype=F32, device=qkv.device)
+    call("egovlp_divided_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(ws), B, T, N, H,
+         mode, C.c_float(q_scale), _stream())
+    return dqkv

@@ -80,6 +80,25 @@ int egovlp_layernorm_bwd(const float* dy, long long lddy, const float* x, long l
                          void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Divided space-time attention core of VarAttention.forward (model/video_transformer.py:104-133) and its
+ * autograd.  Head dim must be 64 (D = 64*H).  mode 0 = time ('b (f n) d -> (b n) f d'), 1 = space ('(b f) n d').
+ *   qkv   bf16 [B*S, 3*D], S = 1 + T*N, columns [q | k | v] each (head, 64); q ALREADY scaled by 64^-0.5
+ *         (the QKV GEMM epilogue applies it, :106)
+ *   out   bf16 [B*S, D]  = cat(cls_out, attended patches) with heads merged (:130-133), ready for proj
+ *   lse   fp32 [B, H, S] log-sum-exp of every query row (saved for the backward)
+ *   cls_part fp32 workspace of egovlp_divided_attn_workspace_floats() floats (CLS-query partials)
+ * Semantics kept from the reference: the CLS query attends over ALL S keys (:112); every patch query attends
+ * over its group's keys plus the CLS key/value (:117-124).
+ * Backward: dqkv bf16 [B*S, 3*D] receives d(q_prescale), dk, dv for every token (q gradient multiplied by
+ * q_scale); dcls_ws is an fp32 workspace of B*H*3*64 floats (zeroed internally).
+ */
+long long egovlp_divided_attn_workspace_floats(int B, int T, int N, int H, int mode);
+int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N, int H,
+                            int mode, void* stream);
+int egovlp_divided_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                            float* dcls_ws, int B, int T, int N, int H, int mode, float q_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers on the path.
  */
 /* fp32 -> bf16 cast (weights: fp32 master -> bf16 GEMM operand). */

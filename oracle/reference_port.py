@@ -39,19 +39,20 @@ def _softmax_av(q, k, v):
     return torch.softmax(q @ k.transpose(-1, -2), dim=-1) @ v
 
 
-def divided_attention(x, p, prefix, heads, frames, patches, mode):
-    """VarAttention.forward (video_transformer.py:100-137) without einops.
+def divided_attention_core(qkv, heads, frames, patches, mode, scale_q=True):
+    """Attention core of VarAttention.forward (video_transformer.py:104-133) without einops.
 
-    x: [B, 1+frames*patches, D] (token 0 = CLS, then frame-major patch tokens).
+    qkv: [B, 1+frames*patches, 3*D] = the qkv Linear's output (token 0 = CLS, then frame-major patches).
     mode 'time'  : each (b, head, patch) attends over its `frames` tokens (+ CLS key/value)
     mode 'space' : each (b, head, frame) attends over its `patches` tokens (+ CLS key/value)
     The CLS query attends over all 1+frames*patches keys in both modes (:112).
+    Returns the head-merged [B, S, D] tensor that feeds `proj`.
     """
-    B, S, D = x.shape
+    B, S, D3 = qkv.shape
+    D = D3 // 3
     d = D // heads
-    qkv = _linear(x, p[prefix + "qkv.weight"], p[prefix + "qkv.bias"])            # :103
     qkv = qkv.reshape(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)                  # 3,B,h,S,d (:104)
-    q, k, v = qkv[0] * (d ** -0.5), qkv[1], qkv[2]                                # :106 (scale on q incl. CLS)
+    q, k, v = qkv[0] * (d ** -0.5 if scale_q else 1.0), qkv[1], qkv[2]            # :106 (scale on q incl. CLS)
     cls_out = _softmax_av(q[:, :, :1], k, v)                                      # :112  [B,h,1,d]
 
     def group(t):  # [B,h,frames*patches,d] -> groups
@@ -66,7 +67,13 @@ def divided_attention(x, p, prefix, heads, frames, patches, mode):
     if mode == "time":
         og = og.transpose(2, 3)                                                   # :127
     out = torch.cat([cls_out, og.reshape(B, heads, frames * patches, d)], dim=2)   # :130
-    out = out.permute(0, 2, 1, 3).reshape(B, S, D)                                # :133
+    return out.permute(0, 2, 1, 3).reshape(B, S, D)                               # :133
+
+
+def divided_attention(x, p, prefix, heads, frames, patches, mode):
+    """VarAttention.forward (video_transformer.py:100-137): qkv Linear -> attention core -> proj Linear."""
+    qkv = _linear(x, p[prefix + "qkv.weight"], p[prefix + "qkv.bias"])            # :103
+    out = divided_attention_core(qkv, heads, frames, patches, mode)
     return _linear(out, p[prefix + "proj.weight"], p[prefix + "proj.bias"])       # :135
 
 

@@ -140,3 +140,28 @@ def test_cast_and_colsum(ops):
         out = torch.ones(768, device="cuda")
         ops.colsum_accum(dy, out)
         assert rel_err(out, 1 + dy.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("B,T,N,H,mode", [(2, 4, 196, 2, 1), (2, 4, 196, 2, 0), (1, 16, 196, 1, 0), (1, 16, 196, 1, 1),
+                                          (2, 3, 4, 2, 0), (2, 3, 4, 2, 1), (3, 8, 50, 1, 0), (2, 1, 30, 1, 0),
+                                          (2, 5, 196, 1, 0)])
+def test_divided_attention_fwd_bwd(ops, B, T, N, H, mode):
+    from oracle import reference_port as rp
+    S, D = 1 + T * N, 64 * H
+    qkv = mk((B * S, 3 * D), 50 + T + mode, 1.0)
+    scale = 0.125
+    qkv[:, :D] *= scale                                       # the QKV GEMM epilogue pre-scales q
+    out, lse = ops.divided_attn_fwd(qkv, B, T, N, H, mode)
+    x = qkv.float().reshape(B, S, 3 * D).clone().requires_grad_(True)
+    ref = rp.divided_attention_core(x, H, T, N, "space" if mode else "time", scale_q=False)
+    assert rel_err(out.reshape(B, S, D), ref) < 6e-3
+    dout = mk((B * S, D), 60 + mode)
+    ref.backward(dout.float().reshape(B, S, D))
+    dqkv = ops.divided_attn_bwd(qkv, out, dout, lse, B, T, N, H, mode, q_scale=1.0)
+    g = x.grad.reshape(B * S, 3 * D)
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        assert rel_err(dqkv[:, sl], g[:, sl]) < 1.5e-2, name
+    # CLS rows on their own (summed over every group)
+    cls = torch.arange(B, device="cuda") * S
+    assert rel_err(dqkv[cls], g[cls]) < 1.5e-2
+    assert rel_err(out[cls], ref.reshape(B * S, D)[cls]) < 6e-3
