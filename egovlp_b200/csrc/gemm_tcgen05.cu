@@ -40,6 +40,7 @@ struct EpiParams {
   float alpha;
   float col_scale;
   int col_scale_ncols;
+  int res_row_mod;  // 0: residual row = m; else residual row = m % res_row_mod (broadcast table)
 };
 
 template <int BLOCK_N>
@@ -236,7 +237,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         if (ep.residual) {
-          const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (long long)row * ep.ldr + n0);
+          const int rrow = ep.res_row_mod ? row % ep.res_row_mod : row;
+          const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + n0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 b = __ldg(r4 + j);
@@ -334,7 +336,7 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   ep.out = e->out; ep.out2 = reinterpret_cast<bf16*>(e->out2);
   ep.ldr = e->ldr; ep.ldaux = e->ldaux; ep.ldo = e->ldo; ep.ldo2 = e->ldo2;
   ep.out_mode = e->out_mode; ep.act = e->act; ep.alpha = e->alpha;
-  ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols;
+  ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols; ep.res_row_mod = e->res_row_mod;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N % 256 == 0) return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
   return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);

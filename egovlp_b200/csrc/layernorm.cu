@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dx,
-                     bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int D) {
+                     long long lddx, bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int rows, int D) {
   __shared__ float red[LN_WARPS][NV * 128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float4 pg[NV], pb[NV], g4[NV];
@@ -109,7 +110,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
         const long long off = (long long)row * D + c;
         if (add1) { const float4 a = *reinterpret_cast<const float4*>(add1 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         if (add2) { const float4 a = *reinterpret_cast<const float4*>(add2 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        if (dx) *reinterpret_cast<float4*>(dx + off) = o;
+        if (dx) *reinterpret_cast<float4*>(dx + (long long)row * lddx + c) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
@@ -187,10 +188,10 @@ int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_ou
 
 template <int NV>
 int launch_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
-                  const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, void* dx16,
-                  float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
+                  const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, long long lddx,
+                  void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 4);
-  layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
+  layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx,
                                                           reinterpret_cast<bf16*>(dx16), dgamma, dbeta, rows, D);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
@@ -217,14 +218,14 @@ extern "C" int egovlp_layernorm_fwd(const float* x, long long ldx, const float* 
 
 extern "C" int egovlp_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx,
                                     const float* gamma, const float* mean, const float* rstd, const float* add1,
-                                    const float* add2, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                                    int rows, int D, void* stream) {
+                                    const float* add2, float* dx, long long lddx, void* dx_bf16, float* dgamma,
+                                    float* dbeta, int rows, int D, void* stream) {
   EGOVLP_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_bf16), "layernorm_bwd: null pointer");
-  EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0, "layernorm_bwd: bad D=%d", D);
+  EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "layernorm_bwd: bad D=%d", D);
   if (rows == 0) return EGOVLP_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (D + 127) / 128;
-#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, dx_bf16, dgamma, dbeta, rows, D, st)
+#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
   switch (nv) { LN_BWD_CASE(1); LN_BWD_CASE(2); LN_BWD_CASE(3); LN_BWD_CASE(4); LN_BWD_CASE(5); LN_BWD_CASE(6); LN_BWD_CASE(7); LN_BWD_CASE(8); }
 #undef LN_BWD_CASE
   return EGOVLP_ERR_UNSUPPORTED;

@@ -1,0 +1,455 @@
+"""Host-side step engine: torch.autograd.Function wrappers that sequence the CUDA kernels of the hot path.
+
+torch supplies device buffers, the current stream and the autograd graph (so DDP / optimizers of the unchanged
+reference trainer keep working); every FLOP below runs in libegovlp_b200.so through `ops`.
+
+Numerics layout: residual stream and LayerNorm statistics in fp32, GEMM operands in bf16 (fp32 accumulation in
+TMEM), attention probabilities never leave the SM, losses in fp32.  fp32 master parameters are the autograd
+leaves; their bf16 GEMM copies come from `Bf16Cache` (refreshed when a parameter's version changes).
+"""
+import torch
+
+from . import ops
+
+BF16, F32 = torch.bfloat16, torch.float32
+Q_SCALE = 0.125            # head_dim ** -0.5 for head_dim = 64 (model/video_transformer.py:87)
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def _zeros(shape, like):
+    return torch.zeros(shape, dtype=F32, device=like.device)
+
+
+class Bf16Cache:
+    """bf16 copies of fp32 parameters, refreshed lazily when the parameter changed (optimizer step / load)."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, p, shape=None):
+        key = id(p)
+        ent = self._store.get(key)
+        if ent is None or ent[0] != p._version or ent[1].device != p.device or ent[2] != p.data_ptr():
+            src = p.detach().contiguous()
+            ent = (p._version, ops.cast_bf16(src), p.data_ptr())
+            self._store[key] = ent
+        t = ent[1]
+        return t.view(shape) if shape is not None else t
+
+    def cat(self, name, params):
+        """bf16 concat along dim 0 of several parameters (DistilBERT q/k/v -> one [3D, D] operand)."""
+        vers = tuple((p._version, p.data_ptr()) for p in params)
+        ent = self._store.get(name)
+        if ent is None or ent[0] != vers:
+            ent = (vers, torch.cat([ops.cast_bf16(p.detach().contiguous()) for p in params], dim=0))
+            self._store[name] = ent
+        return ent[1]
+
+    def clear(self):
+        self._store.clear()
+
+
+# bf16 twins of fp32 gradient tensors handed between consecutive Functions (saves one cast pass per block)
+_twin = {}
+
+
+def _publish_twin(t32, t16):
+    _twin.clear()
+    _twin[(t32.data_ptr(), tuple(t32.shape))] = t16
+
+
+def _bf16_of(t32):
+    t16 = _twin.pop((t32.data_ptr(), tuple(t32.shape)), None)
+    if t16 is None:
+        t16 = ops.cast_bf16(t32.contiguous())
+    return t16
+
+
+def _split_for(n_out, n_in, k_rows):
+    tiles = ((n_out + 127) // 128) * ((n_in + 255) // 256)
+    return max(1, min((k_rows + 63) // 64, round(400 / tiles)))
+
+
+def wgrad(dy16, x16, n_out, n_in):
+    """dW[n_out, n_in] = dy^T x (contraction over token rows), fp32, split-K atomics."""
+    dw = _zeros((n_out, n_in), dy16)
+    ops.gemm(dy16, x16, dw, a_mn=True, b_mn=True, accumulate=True, split_k=_split_for(n_out, n_in, dy16.shape[0]))
+    return dw
+
+
+def bgrad(dy):
+    db = _zeros((dy.shape[1],), dy)
+    ops.colsum_accum(dy, db)
+    return db
+
+
+# ----------------------------------------------------------------------------------------------------------
+# video tower
+# ----------------------------------------------------------------------------------------------------------
+class PatchEmbedFn(torch.autograd.Function):
+    """VideoPatchEmbed + cls/pos/temporal embedding assembly (model/video_transformer.py:72-77, 304-321)."""
+
+    @staticmethod
+    def forward(ctx, video, cls_token, pos_embed, temporal_embed, w, b, cache):
+        B, T, C, H, W = video.shape
+        D, _, P, _ = w.shape
+        N = (H // P) * (W // P)
+        S = 1 + T * N
+        K = C * P * P
+        video = video.contiguous().float()
+        patches = _empty((B * S, K), BF16, video)
+        ops.patch_im2col(video, patches, P)
+        table = _empty((S, D), F32, video)
+        ops.video_pos_table(cls_token.detach().contiguous(), pos_embed.detach().contiguous(),
+                            temporal_embed.detach().contiguous(), b.detach(), table, T, N, D)
+        x = _empty((B * S, D), F32, video)
+        ops.gemm(patches, cache.get(w, (D, K)), x, bias=b.detach(), residual=table, res_row_mod=S)
+        ctx.dims = (B, T, N, D, K, temporal_embed.shape[1])
+        ctx.save_for_backward(patches)
+        return x.view(B, S, D)
+
+    @staticmethod
+    def backward(ctx, dx):
+        (patches,) = ctx.saved_tensors
+        B, T, N, D, K, F = ctx.dims
+        dx = dx.contiguous().view(-1, D)
+        dx16 = _bf16_of(dx)
+        dw = wgrad(dx16, patches, D, K)
+        dcls, dpos = _zeros((1, 1, D), dx), _zeros((1, N + 1, D), dx)
+        dtemp, dbias = _zeros((1, F, D), dx), _zeros((D,), dx)
+        tmp = _empty(((1 + T * N) * D,), F32, dx)
+        ops.video_embed_bwd(dx, tmp, dcls, dpos, dtemp, dbias, B, T, N, D)
+        P = int(round((K // 3) ** 0.5))
+        return None, dcls, dpos, dtemp, dw.view(D, 3, P, P), dbias, None
+
+
+class SpaceTimeBlockFn(torch.autograd.Function):
+    """SpaceTimeBlock.forward (model/video_transformer.py:163-177) incl. both VarAttention calls and the Mlp.
+
+    params: norm1.{w,b}, attn.qkv.{w,b}, attn.proj.{w,b}, timeattn.qkv.{w,b}, timeattn.proj.{w,b},
+            norm2.{w,b}, mlp.fc1.{w,b}, mlp.fc2.{w,b}, norm3.{w,b}      (18 tensors, reference order)
+    """
+
+    @staticmethod
+    def forward(ctx, x, dims, eps, cache, *p):
+        (n1w, n1b, sqw, sqb, spw, spb, tqw, tqb, tpw, tpb, n2w, n2b, f1w, f1b, f2w, f2b, n3w, n3b) = p
+        B, T, N, H = dims
+        D = H * 64
+        S = 1 + T * N
+        M = B * S
+        HID = f1w.shape[0]
+        x2 = x.contiguous().view(M, D)
+        train = any(ctx.needs_input_grad)
+
+        def ln(inp, w, b):
+            y = _empty((M, D), BF16, inp)
+            mean, rstd = _empty((M,), F32, inp), _empty((M,), F32, inp)
+            ops.layernorm_fwd(inp, w.detach(), b.detach(), eps, y16=y, mean=mean, rstd=rstd)
+            return y, mean, rstd
+
+        def attention(inp16, qw, qb, pw, pb, mode, resid):
+            qkv = _empty((M, 3 * D), BF16, inp16)
+            ops.gemm(inp16, cache.get(qw), qkv, bias=qb.detach(), col_scale=Q_SCALE, col_scale_ncols=D)
+            a, lse = ops.divided_attn_fwd(qkv, B, T, N, H, mode)
+            out = _empty((M, D), F32, inp16)
+            ops.gemm(a, cache.get(pw), out, bias=pb.detach(), residual=resid)
+            return qkv, a, lse, out
+
+        n3, mean3, rstd3 = ln(x2, n3w, n3b)
+        qkv_t, a_t, lse_t, tr = attention(n3, tqw, tqb, tpw, tpb, 0, x2)          # time_residual = x + time_output
+        n1, mean1, rstd1 = ln(tr, n1w, n1b)
+        qkv_s, a_s, lse_s, sr = attention(n1, sqw, sqb, spw, spb, 1, x2)          # space_residual = x + space_output
+        n2, mean2, rstd2 = ln(sr, n2w, n2b)
+        h = _empty((M, HID), BF16, x2)
+        u = _empty((M, HID), BF16, x2) if train else None
+        ops.gemm(n2, cache.get(f1w), h, bias=f1b.detach(), act=1, out2=u)
+        y = _empty((M, D), F32, x2)
+        ops.gemm(h, cache.get(f2w), y, bias=f2b.detach(), residual=sr)
+        if train:
+            ctx.dims, ctx.cache = (B, T, N, H, HID), cache
+            ctx.save_for_backward(x2, n3, mean3, rstd3, qkv_t, a_t, lse_t, tr, n1, mean1, rstd1, qkv_s, a_s, lse_s, sr,
+                                  n2, mean2, rstd2, u, h, *p)
+        return y.view(B, S, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        sv = ctx.saved_tensors
+        (x2, n3, mean3, rstd3, qkv_t, a_t, lse_t, tr, n1, mean1, rstd1, qkv_s, a_s, lse_s, sr, n2, mean2, rstd2, u,
+         h) = sv[:20]
+        (n1w, n1b, sqw, sqb, spw, spb, tqw, tqb, tpw, tpb, n2w, n2b, f1w, f1b, f2w, f2b, n3w, n3b) = sv[20:]
+        B, T, N, H, HID = ctx.dims
+        cache = ctx.cache
+        D = H * 64
+        M = x2.shape[0]
+        dy = dy.contiguous().view(M, D)
+        dy16 = _bf16_of(dy)
+
+        # ---- MLP:  y = sr + fc2(gelu(fc1(LN2(sr))))
+        g_f2w, g_f2b = wgrad(dy16, h, D, HID), bgrad(dy)
+        du = _empty((M, HID), BF16, dy)
+        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=2)               # (dy W2) * gelu'(u)
+        g_f1w, g_f1b = wgrad(du, n2, HID, D), bgrad(du)
+        dn2 = _empty((M, D), F32, dy)
+        ops.gemm(du, cache.get(f1w), dn2, b_mn=True)
+        del du
+        dsr, dsr16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
+        g_n2w, g_n2b = _zeros((D,), dy), _zeros((D,), dy)
+        ops.layernorm_bwd(dn2, sr, n2w.detach(), mean2, rstd2, add1=dy, dx=dsr, dx16=dsr16, dgamma=g_n2w, dbeta=g_n2b)
+        del dn2
+
+        def attention_bwd(dres, dres16, qkv, a, lse, inp16, qw, pw, mode):
+            g_pw, g_pb = wgrad(dres16, a, D, D), bgrad(dres)
+            da = _empty((M, D), BF16, dres)
+            ops.gemm(dres16, cache.get(pw), da, b_mn=True)
+            dqkv = ops.divided_attn_bwd(qkv, a, da, lse, B, T, N, H, mode, Q_SCALE)
+            g_qw, g_qb = wgrad(dqkv, inp16, 3 * D, D), bgrad(dqkv)
+            dinp = _empty((M, D), F32, dres)
+            ops.gemm(dqkv, cache.get(qw), dinp, b_mn=True)
+            return g_qw, g_qb, g_pw, g_pb, dinp
+
+        # ---- space attention:  sr = x + proj(attn(LN1(tr)))
+        g_sqw, g_sqb, g_spw, g_spb, dn1 = attention_bwd(dsr, dsr16, qkv_s, a_s, lse_s, n1, sqw, spw, 1)
+        dtr, dtr16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
+        g_n1w, g_n1b = _zeros((D,), dy), _zeros((D,), dy)
+        ops.layernorm_bwd(dn1, tr, n1w.detach(), mean1, rstd1, dx=dtr, dx16=dtr16, dgamma=g_n1w, dbeta=g_n1b)
+        del dn1
+        # ---- time attention:  tr = x + proj(timeattn(LN3(x)))
+        g_tqw, g_tqb, g_tpw, g_tpb, dn3 = attention_bwd(dtr, dtr16, qkv_t, a_t, lse_t, n3, tqw, tpw, 0)
+        dx, dx16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
+        g_n3w, g_n3b = _zeros((D,), dy), _zeros((D,), dy)
+        ops.layernorm_bwd(dn3, x2, n3w.detach(), mean3, rstd3, add1=dsr, add2=dtr, dx=dx, dx16=dx16, dgamma=g_n3w,
+                          dbeta=g_n3b)
+        _publish_twin(dx, dx16)
+        S = 1 + T * N
+        return (dx.view(B, S, D), None, None, None, g_n1w, g_n1b, g_sqw, g_sqb, g_spw, g_spb, g_tqw, g_tqb, g_tpw,
+                g_tpb, g_n2w, g_n2b, g_f1w, g_f1b, g_f2w, g_f2b, g_n3w, g_n3b)
+
+
+class ClsHeadFn(torch.autograd.Function):
+    """norm(x)[:, 0] -> optional Linear projection (model/video_transformer.py:330; model/model.py:77-79,141-142).
+    LayerNorm is applied to the B CLS rows only (the reference normalises all S rows, then slices)."""
+
+    @staticmethod
+    def forward(ctx, x, eps, cache, nw, nb, pw, pb):
+        B, S, D = x.shape
+        x = x.contiguous()
+        cls_rows = x.view(B, S * D)[:, :D]                      # row stride S*D
+        y16 = _empty((B, D), BF16, x)
+        y32 = _empty((B, D), F32, x)
+        mean, rstd = _empty((B,), F32, x), _empty((B,), F32, x)
+        ops.layernorm_fwd(cls_rows, nw.detach(), nb.detach(), eps, y16=y16, y32=y32, mean=mean, rstd=rstd)
+        ctx.has_proj = pw is not None
+        ctx.shape, ctx.cache = (B, S, D), cache
+        if pw is None:
+            ctx.save_for_backward(x, mean, rstd, nw)
+            return y32
+        out = _empty((B, pw.shape[0]), F32, x)
+        ops.gemm(y16, cache.get(pw), out, bias=pb.detach())
+        ctx.save_for_backward(x, mean, rstd, nw, y16, pw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, S, D = ctx.shape
+        dout = dout.contiguous().float()
+        g_pw = g_pb = None
+        if ctx.has_proj:
+            x, mean, rstd, nw, y16, pw = ctx.saved_tensors
+            Pd = pw.shape[0]
+            d16 = ops.cast_bf16(dout)
+            g_pw, g_pb = wgrad(d16, y16, Pd, D), bgrad(dout)
+            dn = _empty((B, D), F32, dout)
+            ops.gemm(d16, ctx.cache.get(pw), dn, b_mn=True)
+        else:
+            x, mean, rstd, nw = ctx.saved_tensors
+            dn = dout
+        dx = _zeros((B, S, D), dout)
+        g_nw, g_nb = _zeros((D,), dout), _zeros((D,), dout)
+        ops.layernorm_bwd(dn, x.view(B, S * D)[:, :D], nw.detach(), mean, rstd, dx=dx.view(B, S * D)[:, :D],
+                          dgamma=g_nw, dbeta=g_nb)
+        return dx, None, None, g_nw, g_nb, g_pw, g_pb
+
+
+# ----------------------------------------------------------------------------------------------------------
+# text tower (DistilBERT) + ReLU/Linear projection
+# ----------------------------------------------------------------------------------------------------------
+class TextTowerFn(torch.autograd.Function):
+    """DistilBertModel(...).last_hidden_state -> (CLS | all tokens) -> ReLU -> Linear  (model/model.py:117-138).
+
+    params: word_emb, pos_emb, emb_ln.{w,b}, then per layer
+            q.{w,b}, k.{w,b}, v.{w,b}, out.{w,b}, sa_ln.{w,b}, lin1.{w,b}, lin2.{w,b}, out_ln.{w,b}   (16 / layer),
+            finally txt_proj.{w,b}.
+    Dropout of the HF model is not applied (deterministic parity path)."""
+
+    @staticmethod
+    def forward(ctx, input_ids, attention_mask, heads, eps, tokens_mode, cache, *p):
+        word, pos, elw, elb = p[:4]
+        pw, pb = p[-2:]
+        layers = [p[4 + 16 * i: 4 + 16 * (i + 1)] for i in range((len(p) - 6) // 16)]
+        B, L = input_ids.shape
+        D = word.shape[1]
+        M = B * L
+        ids = input_ids.contiguous().to(torch.int64)
+        mask = attention_mask.contiguous().to(torch.int64)
+        dev = word
+        train = any(ctx.needs_input_grad)
+        saved = []
+
+        emb = _empty((M, D), F32, dev)
+        ops.text_embed_fwd(ids, word.detach(), pos.detach(), emb, B, L, D)
+        x, x16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
+        mean, rstd = _empty((M,), F32, dev), _empty((M,), F32, dev)
+        ops.layernorm_fwd(emb, elw.detach(), elb.detach(), eps, y16=x16, y32=x, mean=mean, rstd=rstd)
+        saved += [emb, mean, rstd]
+        for li, lp in enumerate(layers):
+            (qw, qb, kw, kb, vw, vb, ow, ob, sw, sb, l1w, l1b, l2w, l2b, fw, fb) = lp
+            wqkv = cache.cat(("text_qkv_w", li, id(qw)), (qw, kw, vw))
+            bqkv = torch.cat([qb.detach(), kb.detach(), vb.detach()])
+            HID = l1w.shape[0]
+            qkv = _empty((M, 3 * D), BF16, dev)
+            ops.gemm(x16, wqkv, qkv, bias=bqkv, col_scale=Q_SCALE, col_scale_ncols=D)
+            ctxv = _empty((M, D), BF16, dev)
+            ops.text_attn_fwd(qkv, mask, ctxv, B, L, heads)
+            sa = _empty((M, D), F32, dev)
+            ops.gemm(ctxv, cache.get(ow), sa, bias=ob.detach(), residual=x)               # sa_output + x
+            x1, x1_16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
+            m1, r1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+            ops.layernorm_fwd(sa, sw.detach(), sb.detach(), eps, y16=x1_16, y32=x1, mean=m1, rstd=r1)
+            hh, u = _empty((M, HID), BF16, dev), (_empty((M, HID), BF16, dev) if train else None)
+            ops.gemm(x1_16, cache.get(l1w), hh, bias=l1b.detach(), act=1, out2=u)
+            ff = _empty((M, D), F32, dev)
+            ops.gemm(hh, cache.get(l2w), ff, bias=l2b.detach(), residual=x1)              # ffn_output + sa_output
+            xn, xn16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
+            m2, r2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
+            ops.layernorm_fwd(ff, fw.detach(), fb.detach(), eps, y16=xn16, y32=xn, mean=m2, rstd=r2)
+            saved += [x16, qkv, ctxv, sa, m1, r1, x1_16, u, hh, ff, m2, r2]
+            x, x16 = xn, xn16
+        rows, stride = (M, D) if tokens_mode else (B, L * D)
+        r16 = _empty((rows, D), BF16, dev)
+        ops.relu_rows_fwd(x, stride, r16, rows, D)
+        out = _empty((rows, pw.shape[0]), F32, dev)
+        ops.gemm(r16, cache.get(pw), out, bias=pb.detach())
+        if train:
+            ctx.meta = (B, L, D, heads, tokens_mode, len(layers), len(saved))
+            ctx.cache = cache
+            ctx.save_for_backward(ids, mask, x, r16, *saved, *p)
+        return out.view(B, L, -1) if tokens_mode else out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, L, D, heads, tokens_mode, n_layers, n_saved = ctx.meta
+        cache = ctx.cache
+        sv = ctx.saved_tensors
+        ids, mask, x_last, r16 = sv[:4]
+        saved = list(sv[4:4 + n_saved])
+        p = sv[4 + n_saved:]
+        word, pos, elw, elb = p[:4]
+        pw, pb = p[-2:]
+        layers = [p[4 + 16 * i: 4 + 16 * (i + 1)] for i in range(n_layers)]
+        M = B * L
+        Pd = pw.shape[0]
+        rows, stride = (M, D) if tokens_mode else (B, L * D)
+        dout = dout.contiguous().float().view(rows, Pd)
+        d16 = ops.cast_bf16(dout)
+        g_pw, g_pb = wgrad(d16, r16, Pd, D), bgrad(dout)
+        dr = _empty((rows, D), F32, dout)
+        ops.gemm(d16, cache.get(pw), dr, b_mn=True)
+        dx = _zeros((M, D), dout)
+        ops.relu_rows_bwd(x_last, stride, dr, dx, rows, D)
+        grads = []
+        for li in reversed(range(n_layers)):
+            (qw, qb, kw, kb, vw, vb, ow, ob, sw, sb, l1w, l1b, l2w, l2b, fw, fb) = layers[li]
+            x16, qkv, ctxv, sa, m1, r1, x1_16, u, hh, ff, m2, r2 = saved[3 + 12 * li: 3 + 12 * (li + 1)]
+            HID = l1w.shape[0]
+            dff, dff16 = _empty((M, D), F32, dout), _empty((M, D), BF16, dout)
+            g_fw, g_fb = _zeros((D,), dout), _zeros((D,), dout)
+            ops.layernorm_bwd(dx, ff, fw.detach(), m2, r2, dx=dff, dx16=dff16, dgamma=g_fw, dbeta=g_fb)
+            g_l2w, g_l2b = wgrad(dff16, hh, D, HID), bgrad(dff)
+            du = _empty((M, HID), BF16, dout)
+            ops.gemm(dff16, cache.get(l2w), du, b_mn=True, aux=u, act=2)
+            g_l1w, g_l1b = wgrad(du, x1_16, HID, D), bgrad(du)
+            dx1 = _empty((M, D), F32, dout)
+            ops.gemm(du, cache.get(l1w), dx1, b_mn=True, residual=dff)                     # + residual path
+            dsa, dsa16 = _empty((M, D), F32, dout), _empty((M, D), BF16, dout)
+            g_sw, g_sb = _zeros((D,), dout), _zeros((D,), dout)
+            ops.layernorm_bwd(dx1, sa, sw.detach(), m1, r1, dx=dsa, dx16=dsa16, dgamma=g_sw, dbeta=g_sb)
+            g_ow, g_ob = wgrad(dsa16, ctxv, D, D), bgrad(dsa)
+            dctx = _empty((M, D), BF16, dout)
+            ops.gemm(dsa16, cache.get(ow), dctx, b_mn=True)
+            dqkv = _empty((M, 3 * D), BF16, dout)
+            ops.text_attn_bwd(qkv, mask, dctx, dqkv, B, L, heads, Q_SCALE)
+            g_wqkv, g_bqkv = wgrad(dqkv, x16, 3 * D, D), bgrad(dqkv)
+            wqkv = cache.cat(("text_qkv_w", li, id(qw)), (qw, kw, vw))
+            dxin = _empty((M, D), F32, dout)
+            ops.gemm(dqkv, wqkv, dxin, b_mn=True, residual=dsa)                            # x feeds qkv and the residual
+            dx = dxin
+            gq, gk, gv = g_wqkv[:D], g_wqkv[D:2 * D], g_wqkv[2 * D:]
+            bq, bk, bv = g_bqkv[:D], g_bqkv[D:2 * D], g_bqkv[2 * D:]
+            grads = [gq, bq, gk, bk, gv, bv, g_ow, g_ob, g_sw, g_sb, g_l1w, g_l1b, g_l2w, g_l2b, g_fw, g_fb] + grads
+        emb, mean, rstd = saved[:3]
+        demb = _empty((M, D), F32, dout)
+        g_elw, g_elb = _zeros((D,), dout), _zeros((D,), dout)
+        ops.layernorm_bwd(dx, emb, elw.detach(), mean, rstd, dx=demb, dgamma=g_elw, dbeta=g_elb)
+        g_word, g_pos = torch.zeros_like(word), torch.zeros_like(pos)
+        ops.text_embed_bwd(ids, demb, g_word, g_pos, B, L, D)
+        return (None, None, None, None, None, None, g_word, g_pos, g_elw, g_elb, *grads, g_pw, g_pb)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# similarity + losses
+# ----------------------------------------------------------------------------------------------------------
+class SimMatrixFn(torch.autograd.Function):
+    """sim_matrix (model/model.py:189-197): cosine similarity with the norm clamped at eps, fp32."""
+
+    @staticmethod
+    def forward(ctx, a, b, eps):
+        a, b = a.contiguous().float(), b.contiguous().float()
+        an, na = ops.rownorm_fwd(a, eps)
+        bn, nb = ops.rownorm_fwd(b, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(an, na, bn, nb)
+        return ops.sgemm(an, bn)
+
+    @staticmethod
+    def backward(ctx, dx):
+        an, na, bn, nb = ctx.saved_tensors
+        dx = dx.contiguous().float()
+        dan = ops.sgemm(dx, bn, trans_b=False)                    # dX @ bn
+        dbn = ops.sgemm(dx, an, trans_a=True, trans_b=False)      # dX^T @ an
+        return ops.rownorm_bwd(dan, an, na, ctx.eps), ops.rownorm_bwd(dbn, bn, nb, ctx.eps), None
+
+
+class NceLossFn(torch.autograd.Function):
+    """EgoNCE / InfoNCE on a similarity matrix with a uint8 positives mask (model/loss.py:13-25, 34-53)."""
+
+    @staticmethod
+    def forward(ctx, x, mask, temperature):
+        x = x.contiguous().float()
+        loss, stats = ops.nce_fwd(x, mask, 1.0 / temperature)
+        ctx.inv_temp = 1.0 / temperature
+        ctx.save_for_backward(x, mask, stats)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mask, stats = ctx.saved_tensors
+        return ops.nce_bwd(x, mask, stats, ctx.inv_temp, g.contiguous().float()), None, None
+
+
+class MaxMarginFn(torch.autograd.Function):
+    """MaxMarginRankingLoss (model/loss.py:63-90), no host-side index building."""
+
+    @staticmethod
+    def forward(ctx, x, margin, fix_norm):
+        x = x.contiguous().float()
+        ctx.args = (margin, fix_norm)
+        ctx.save_for_backward(x)
+        return ops.maxmargin_fwd(x, margin, fix_norm)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.maxmargin_bwd(x, ctx.args[0], ctx.args[1], g.contiguous().float()), None, None

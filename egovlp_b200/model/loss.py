@@ -1,0 +1,51 @@
+"""Losses of the reference's model/loss.py on CUDA kernels: same class names, constructor arguments and
+forward signatures.  AdaptiveMaxMarginRankingLoss / CrossEntropy are outside the hot-path scope."""
+import torch
+from torch import nn
+
+from .. import engine, ops
+
+
+class NormSoftmaxLoss(nn.Module):
+    def __init__(self, temperature=0.05):
+        super().__init__()
+        self.temperature = temperature
+
+    def forward(self, x):
+        G = x.shape[0]
+        assert x.shape == (G, G)
+        mask = ops.positives_mask_from_sims(None, None, G, 0) if x.is_cuda else None
+        return engine.NceLossFn.apply(x, mask, self.temperature)
+
+
+class EgoNCE(nn.Module):
+    def __init__(self, temperature=0.05, noun=True, verb=True):
+        super().__init__()
+        self.noun, self.verb, self.temperature = noun, verb, temperature
+
+    def _mode(self):
+        return 1 if (self.noun and self.verb) else 2 if self.noun else 3
+
+    def forward(self, x, mask_v, mask_n):
+        """x, mask_v (= sim_matrix(verb, verb)), mask_n (= sim_matrix(noun, noun)): [G, G] float, as the
+        unchanged trainer passes them (trainer/trainer_egoclip.py:132-135)."""
+        G = x.shape[0]
+        mask = ops.positives_mask_from_sims(mask_v.detach().contiguous().float(), mask_n.detach().contiguous().float(),
+                                            G, self._mode())
+        return engine.NceLossFn.apply(x, mask, self.temperature)
+
+    def fused(self, text_embeds, video_embeds, verb_vec, noun_vec):
+        """B200-first entry: gathered embeddings + multi-hot tags -> loss, without materialising the
+        verb/noun similarity matrices (positives from bit-packed tag co-occurrence)."""
+        mask = ops.positives_mask_from_tags(verb_vec, noun_vec, self._mode())
+        x = engine.SimMatrixFn.apply(text_embeds, video_embeds, 1e-8)
+        return engine.NceLossFn.apply(x, mask, self.temperature)
+
+
+class MaxMarginRankingLoss(nn.Module):
+    def __init__(self, margin=0.2, fix_norm=True):
+        super().__init__()
+        self.fix_norm, self.margin = fix_norm, margin
+
+    def forward(self, x, weight=None):
+        return engine.MaxMarginFn.apply(x, self.margin, self.fix_norm)

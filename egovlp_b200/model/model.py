@@ -1,0 +1,186 @@
+"""FrozenInTime dual encoder + sim_matrix on the B200 kernels.
+
+API mirror of the reference's model/model.py: FrozenInTime(video_params, text_params, projection_dim,
+load_checkpoint, projection, load_temporal_fix), forward(data, video_only, return_embeds), compute_text,
+compute_text_tokens, compute_video, set_device, sim_matrix(a, b, eps) -- and identical state_dict keys
+(SURVEY.md section 8b), so reference checkpoints load and the unchanged trainer drives it.
+"""
+import os
+import warnings
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import engine
+from .video_transformer import SpaceTimeTransformer
+
+
+def state_dict_data_parallel_fix(load_state_dict, curr_state_dict):
+    """Strip / add the DataParallel 'module.' prefix so that `load` matches `curr` (reference utils/util.py:25-51)."""
+    load_keys, curr_keys = list(load_state_dict.keys()), list(curr_state_dict.keys())
+    if not load_keys or not curr_keys:
+        return load_state_dict
+    have, want = load_keys[0].startswith('module.'), curr_keys[0].startswith('module.')
+    if have and not want:
+        return type(load_state_dict)((k[len('module.'):], v) for k, v in load_state_dict.items())
+    if want and not have:
+        return type(load_state_dict)(('module.' + k, v) for k, v in load_state_dict.items())
+    return load_state_dict
+
+
+class BaseModel(nn.Module):
+    """Reference base/base_model.py: __str__ appends the trainable-parameter count."""
+
+    def __str__(self):
+        n = sum(int(np.prod(p.size())) for p in self.parameters() if p.requires_grad)
+        return super().__str__() + '\nTrainable parameters: {}'.format(n)
+
+
+def _build_distilbert(text_params):
+    """Parameter container for the text tower: HuggingFace DistilBertModel (weights only; its forward is not used).
+    Loads the pretrained files when present, otherwise random-initialises the same architecture."""
+    from transformers import DistilBertConfig, DistilBertModel
+    cache_dir = 'pretrained/distilbert-base-uncased'
+    try:
+        from transformers import AutoModel
+        return AutoModel.from_pretrained('distilbert-base-uncased', cache_dir=cache_dir, local_files_only=True)
+    except Exception:  # no network / no files: synthetic-weights path
+        warnings.warn("distilbert-base-uncased files not found: text tower is randomly initialised")
+        return DistilBertModel(DistilBertConfig())
+
+
+class FrozenInTime(BaseModel):
+    def __init__(self, video_params, text_params, projection_dim=256, load_checkpoint=None, projection='minimal',
+                 load_temporal_fix='zeros'):
+        super().__init__()
+        self.video_params = video_params
+        self.text_params = text_params
+        self.load_temporal_fix = load_temporal_fix
+        if not text_params['pretrained']:
+            raise NotImplementedError("Huggingface text models require pretrained init.")
+        if not self.text_params['model'].startswith('distilbert'):
+            raise NotImplementedError(f"{text_params['model']}: only the DistilBERT text tower is implemented")
+        self.text_model = _build_distilbert(text_params)
+        self.text_model.train()
+
+        if video_params['model'] != "SpaceTimeTransformer":
+            raise NotImplementedError(f"{video_params['model']} not implemented")
+        num_frames = video_params.get('num_frames', 4)
+        time_init = video_params.get('time_init', 'zeros')
+        attention_style = video_params.get('attention_style', 'frozen-in-time')
+        arch_config = video_params.get('arch_config', 'base_patch16_224')
+        if arch_config != 'base_patch16_224':
+            raise NotImplementedError
+        model = SpaceTimeTransformer(num_frames=num_frames, time_init=time_init, attention_style=attention_style)
+        model.head = nn.Identity()
+        model.pre_logits = nn.Identity()
+        ftr_dim = model.embed_dim
+        if load_checkpoint in ["", None]:
+            vit_path = "pretrained/jx_vit_base_p16_224-80ecf9dd.pth"
+            if os.path.exists(vit_path):
+                vit_checkpoint = torch.load(vit_path, map_location="cpu")
+                model.load_state_dict(state_dict_data_parallel_fix(vit_checkpoint, model.state_dict()), strict=False)
+            else:
+                warnings.warn(f"{vit_path} not found: video tower keeps its random initialisation")
+        self.video_model = model
+        self.video_model.fc = nn.Identity()
+
+        if projection == 'minimal':
+            txt_proj = nn.Sequential(nn.ReLU(), nn.Linear(self.text_model.config.hidden_size, projection_dim))
+            vid_proj = nn.Sequential(nn.Linear(ftr_dim, projection_dim))
+        elif projection == '':
+            txt_proj, vid_proj = nn.Identity(), nn.Identity()
+        else:
+            raise NotImplementedError
+        self.txt_proj = txt_proj
+        self.vid_proj = vid_proj
+        object.__setattr__(self, "_bf16_cache", self.video_model._bf16_cache)
+
+        if load_checkpoint not in ["", None]:
+            local_rank = int(os.environ.get('LOCAL_RANK', 0))
+            map_loc = 'cuda:{}'.format(local_rank) if torch.cuda.is_available() else 'cpu'
+            checkpoint = torch.load(load_checkpoint, map_location=map_loc, weights_only=False)
+            state_dict = checkpoint['state_dict']
+            new_state_dict = state_dict_data_parallel_fix(state_dict, self.state_dict())
+            new_state_dict = self._inflate_positional_embeds(new_state_dict)
+            self.load_state_dict(new_state_dict, strict=True)
+
+    def set_device(self, device):
+        self.device = device
+
+    def forward(self, data, video_only=False, return_embeds=True):
+        if video_only:
+            return self.compute_video(data['video'])
+        text_embeddings = self.compute_text(data['text'])
+        video_embeddings = self.compute_video(data['video'])
+        if return_embeds:
+            return text_embeddings, video_embeddings
+        return sim_matrix(text_embeddings, video_embeddings)
+
+    # ---- text ------------------------------------------------------------------------------------------------
+    def _text_params(self):
+        tm = self.text_model
+        p = [tm.embeddings.word_embeddings.weight, tm.embeddings.position_embeddings.weight,
+             tm.embeddings.LayerNorm.weight, tm.embeddings.LayerNorm.bias]
+        for layer in tm.transformer.layer:
+            a, f = layer.attention, layer.ffn
+            for lin in (a.q_lin, a.k_lin, a.v_lin, a.out_lin):
+                p += [lin.weight, lin.bias]
+            p += [layer.sa_layer_norm.weight, layer.sa_layer_norm.bias, f.lin1.weight, f.lin1.bias, f.lin2.weight,
+                  f.lin2.bias, layer.output_layer_norm.weight, layer.output_layer_norm.bias]
+        return p
+
+    def _text(self, text_data, tokens_mode):
+        if not isinstance(self.txt_proj, nn.Sequential):
+            raise NotImplementedError("projection='' is not implemented for the text tower")
+        proj = self.txt_proj[1]
+        cfg = self.text_model.config
+        return engine.TextTowerFn.apply(text_data['input_ids'], text_data['attention_mask'], cfg.n_heads, 1e-12,
+                                        tokens_mode, self._bf16_cache, *self._text_params(), proj.weight, proj.bias)
+
+    def compute_text(self, text_data):
+        return self._text(text_data, False)
+
+    def compute_text_tokens(self, text_data):
+        return self._text(text_data, True)
+
+    # ---- video -----------------------------------------------------------------------------------------------
+    def compute_video(self, video_data):
+        proj = self.vid_proj[0] if isinstance(self.vid_proj, nn.Sequential) else None
+        return self.video_model.forward_features(video_data, proj=proj)
+
+    # ---- checkpoint compat -----------------------------------------------------------------------------------
+    def _inflate_positional_embeds(self, new_state_dict):
+        """Load a checkpoint trained with a different number of frames (reference :145-187): truncate, or extend
+        with zeros / nearest / bilinear interpolation along the frame axis."""
+        key = 'video_model.temporal_embed'
+        curr = self.state_dict()
+        if key in new_state_dict and key in curr:
+            load_te = new_state_dict[key]
+            load_f, curr_f = load_te.shape[1], self.video_params['num_frames']
+            if load_f > curr_f:
+                new_state_dict[key] = load_te[:, :curr_f, :]
+            elif load_f < curr_f:
+                if self.load_temporal_fix == 'zeros':
+                    new_te = torch.zeros([load_te.shape[0], curr_f, load_te.shape[2]], dtype=load_te.dtype,
+                                         device=load_te.device)
+                    new_te[:, :load_f] = load_te
+                elif self.load_temporal_fix in ['interp', 'bilinear']:
+                    mode = 'bilinear' if self.load_temporal_fix == 'bilinear' else 'nearest'
+                    kw = dict(align_corners=True) if mode == 'bilinear' else {}
+                    new_te = F.interpolate(load_te.unsqueeze(0), (curr_f, load_te.shape[2]), mode=mode, **kw).squeeze(0)
+                else:
+                    raise NotImplementedError
+                new_state_dict[key] = new_te
+        key = 'video_model.pos_embed'
+        if key in new_state_dict and key in curr and new_state_dict[key].shape[1] != curr[key].shape[1]:
+            raise NotImplementedError(
+                'Loading models with different spatial resolution / patch number not yet implemented, sorry.')
+        return new_state_dict
+
+
+def sim_matrix(a, b, eps=1e-8):
+    """Cosine similarity a_n @ b_n^T with norms clamped at eps (reference model/model.py:189-197)."""
+    return engine.SimMatrixFn.apply(a, b, eps)

@@ -22,7 +22,7 @@ def _chk(t, dtype, name):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, out2=None, act=0, alpha=1.0,
-         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1):
+         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0):
     """out = epi(A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, last-dim contiguous.
     out: bf16 or fp32 [M,N]; accumulate=True -> fp32 atomic add into `out` (required for split_k>1)."""
     _chk(a, BF16, "a"); _chk(b, BF16, "b")
@@ -44,7 +44,8 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     if bias is not None:
         _chk(bias, F32, "bias"); assert bias.numel() == N
     if residual is not None:
-        _chk(residual, F32, "residual"); assert residual.shape == (M, N)
+        _chk(residual, F32, "residual")
+        assert residual.shape == ((res_row_mod or M), N) and residual.stride(1) == 1
     if aux is not None:
         _chk(aux, BF16, "aux"); assert aux.shape == (M, N)
     if out2 is not None:
@@ -55,6 +56,7 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     else:
         e.out_mode = 0 if out.dtype == BF16 else 1
     e.act, e.alpha, e.col_scale, e.col_scale_ncols = act, alpha, col_scale, col_scale_ncols
+    e.res_row_mod = res_row_mod
     call("egovlp_gemm_bf16", _ptr(a), int(a_mn), C.c_longlong(a.stride(0)), _ptr(b), int(b_mn),
          C.c_longlong(b.stride(0)), M, N, K, C.byref(e), split_k, _stream())
     return out
@@ -76,12 +78,13 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx
     _chk(dy, F32, "dy"); _chk(x, F32, "x")
     rows, D = x.shape
     assert dy.shape == (rows, D) and dy.stride(1) == 1 and x.stride(1) == 1
-    for t in (add1, add2, dx):
+    for t in (add1, add2):
         assert t is None or (t.dtype == F32 and t.is_contiguous() and t.shape == (rows, D))
+    assert dx is None or (dx.dtype == F32 and dx.shape == (rows, D) and dx.stride(1) == 1)
     assert dx16 is None or (dx16.dtype == BF16 and dx16.is_contiguous() and dx16.shape == (rows, D))
     call("egovlp_layernorm_bwd", _ptr(dy), C.c_longlong(dy.stride(0)), _ptr(x), C.c_longlong(x.stride(0)),
-         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1), _ptr(add2), _ptr(dx), _ptr(dx16), _ptr(dgamma),
-         _ptr(dbeta), rows, D, _stream())
+         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1), _ptr(add2), _ptr(dx),
+         C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, D, _stream())
 
 
 def cast_bf16(src, dst=None):
@@ -123,3 +126,152 @@ def divided_attn_bwd(qkv, out, dout, lse, B, T, N, H, mode, q_scale, dqkv=None):
     call("egovlp_divided_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(ws), B, T, N, H,
          mode, C.c_float(q_scale), _stream())
     return dqkv
+
+
+# ---------------------------------------------------------------- video front end
+def patch_im2col(video, patches, P):
+    _chk(video, F32, "video")
+    B, T, Cc, H, W = video.shape
+    assert video.is_contiguous() and patches.dtype == BF16 and patches.is_contiguous()
+    call("egovlp_patch_im2col", _ptr(video), _ptr(patches), B, T, Cc, H, W, P, _stream())
+
+
+def video_pos_table(cls_token, pos_embed, temporal_embed, conv_bias, table, T, N, D):
+    call("egovlp_video_pos_table", _ptr(cls_token), _ptr(pos_embed), _ptr(temporal_embed), _ptr(conv_bias),
+         _ptr(table), T, N, D, _stream())
+
+
+def video_embed_bwd(dx, tmp, dcls, dpos, dtemporal, dbias, B, T, N, D):
+    call("egovlp_video_embed_bwd", _ptr(dx), _ptr(tmp), _ptr(dcls), _ptr(dpos), _ptr(dtemporal), _ptr(dbias), B, T, N,
+         D, _stream())
+
+
+# ---------------------------------------------------------------- text tower pieces
+def text_embed_fwd(ids, word, pos, out, B, L, D):
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    call("egovlp_text_embed_fwd", _ptr(ids), _ptr(word), _ptr(pos), _ptr(out), B, L, D, _stream())
+
+
+def text_embed_bwd(ids, dsum, dword, dpos, B, L, D):
+    call("egovlp_text_embed_bwd", _ptr(ids), _ptr(dsum), _ptr(dword), _ptr(dpos), B, L, D, _stream())
+
+
+def text_attn_fwd(qkv, mask, out, B, L, H):
+    assert mask.dtype == torch.int64 and mask.is_contiguous()
+    call("egovlp_text_attn_fwd", _ptr(qkv), _ptr(mask), _ptr(out), B, L, H, _stream())
+
+
+def text_attn_bwd(qkv, mask, dout, dqkv, B, L, H, q_scale):
+    call("egovlp_text_attn_bwd", _ptr(qkv), _ptr(mask), _ptr(dout), _ptr(dqkv), B, L, H, C.c_float(q_scale), _stream())
+
+
+def relu_rows_fwd(x, row_stride, out, rows, D):
+    call("egovlp_relu_rows_fwd", _ptr(x), C.c_longlong(row_stride), _ptr(out), rows, D, _stream())
+
+
+def relu_rows_bwd(x, row_stride, dh, dx, rows, D):
+    call("egovlp_relu_rows_bwd", _ptr(x), C.c_longlong(row_stride), _ptr(dh), _ptr(dx), rows, D, _stream())
+
+
+# ---------------------------------------------------------------- similarity / losses (fp32)
+def rownorm_fwd(a, eps=1e-8):
+    _chk(a, F32, "a")
+    a = a.contiguous()
+    an, norm = torch.empty_like(a), torch.empty(a.shape[0], dtype=F32, device=a.device)
+    call("egovlp_rownorm_fwd", _ptr(a), _ptr(an), _ptr(norm), a.shape[0], a.shape[1], C.c_float(eps), _stream())
+    return an, norm
+
+
+def rownorm_bwd(dan, an, norm, eps=1e-8):
+    da = torch.empty_like(an)
+    call("egovlp_rownorm_bwd", _ptr(dan.contiguous()), _ptr(an), _ptr(norm), _ptr(da), an.shape[0], an.shape[1],
+         C.c_float(eps), _stream())
+    return da
+
+
+def sgemm(a, b, *, trans_a=False, trans_b=True, out=None, alpha=1.0, beta=0.0):
+    """fp32 C = op(a) @ op(b)^T-style product on CUDA cores.  Default: a[M,K] @ b[N,K]^T.
+    trans_a: a is [K,M]; trans_b=False: b is [K,N]."""
+    _chk(a, F32, "a"); _chk(b, F32, "b")
+    M, K = (a.shape[1], a.shape[0]) if trans_a else a.shape
+    N = b.shape[0] if trans_b else b.shape[1]
+    sam, sak = (a.stride(1), a.stride(0)) if trans_a else (a.stride(0), a.stride(1))
+    sbn, sbk = (b.stride(0), b.stride(1)) if trans_b else (b.stride(1), b.stride(0))
+    if out is None:
+        out = torch.empty(M, N, dtype=F32, device=a.device)
+    call("egovlp_sgemm_f32", _ptr(a), C.c_longlong(sam), C.c_longlong(sak), _ptr(b), C.c_longlong(sbn),
+         C.c_longlong(sbk), _ptr(out), C.c_longlong(out.stride(0)), M, N, K, C.c_float(alpha), C.c_float(beta), _stream())
+    return out
+
+
+def positives_mask_from_tags(verb, noun, mode):
+    """uint8 [G,G] positives mask (diag | shared verb & shared noun) from multi-hot vectors."""
+    G = (verb if verb is not None else noun).shape[0]
+    dev = (verb if verb is not None else noun).device
+    mask = torch.empty(G, G, dtype=torch.uint8, device=dev)
+    vb = nb = None
+    nv = nn_ = 0
+    if verb is not None:
+        nv = verb.shape[1]
+        vb = torch.empty(G, (nv + 31) // 32, dtype=torch.int32, device=dev)
+        call("egovlp_pack_multihot", _ptr(verb.contiguous().float()), _ptr(vb), G, nv, _stream())
+    if noun is not None:
+        nn_ = noun.shape[1]
+        nb = torch.empty(G, (nn_ + 31) // 32, dtype=torch.int32, device=dev)
+        call("egovlp_pack_multihot", _ptr(noun.contiguous().float()), _ptr(nb), G, nn_, _stream())
+    call("egovlp_mask_from_bits", _ptr(vb), nv, _ptr(nb), nn_, _ptr(mask), G, mode, _stream())
+    return mask
+
+
+def positives_mask_from_sims(sim_v, sim_n, G, mode):
+    dev = (sim_v if sim_v is not None else sim_n).device if (sim_v is not None or sim_n is not None) else "cuda"
+    mask = torch.empty(G, G, dtype=torch.uint8, device=dev)
+    call("egovlp_mask_from_sims", _ptr(sim_v), _ptr(sim_n), _ptr(mask), G, mode, _stream())
+    return mask
+
+
+def nce_fwd(x, mask, inv_temp):
+    _chk(x, F32, "x")
+    G = x.shape[0]
+    assert x.shape == (G, G) and x.is_contiguous() and mask.shape == (G, G)
+    stats = torch.empty(4 * G, dtype=F32, device=x.device)
+    loss = torch.empty((), dtype=F32, device=x.device)
+    call("egovlp_nce_fwd", _ptr(x), _ptr(mask), G, C.c_float(inv_temp), _ptr(stats), _ptr(loss), _stream())
+    return loss, stats
+
+
+def nce_bwd(x, mask, stats, inv_temp, gscale):
+    dx = torch.empty_like(x)
+    call("egovlp_nce_bwd", _ptr(x), _ptr(mask), _ptr(stats), x.shape[0], C.c_float(inv_temp), _ptr(gscale), _ptr(dx),
+         _stream())
+    return dx
+
+
+def maxmargin_fwd(x, margin, fix_norm):
+    loss = torch.empty((), dtype=F32, device=x.device)
+    call("egovlp_maxmargin_fwd", _ptr(x), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(loss), _stream())
+    return loss
+
+
+def maxmargin_bwd(x, margin, fix_norm, gscale):
+    dx = torch.empty_like(x)
+    call("egovlp_maxmargin_bwd", _ptr(x), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(gscale), _ptr(dx), _stream())
+    return dx
+
+
+def dual_softmax(sim, temp=500.0):
+    _chk(sim, F32, "sim")
+    sim = sim.contiguous()
+    out = torch.empty_like(sim)
+    call("egovlp_dual_softmax", _ptr(sim), _ptr(out), sim.shape[0], sim.shape[1], C.c_float(temp), _stream())
+    return out
+
+
+def egomcq_score(text, video, eps=1e-8):
+    _chk(text, F32, "text"); _chk(video, F32, "video")
+    Q, K, Cc = video.shape
+    scores = torch.empty(Q, K, dtype=F32, device=text.device)
+    pred = torch.empty(Q, dtype=torch.int64, device=text.device)
+    call("egovlp_egomcq_score", _ptr(text.contiguous()), _ptr(video.contiguous()), _ptr(scores), _ptr(pred), Q, K, Cc,
+         C.c_float(eps), _stream())
+    return scores, pred

@@ -22,6 +22,11 @@ def model_dims(embed_dim=768, depth=12, heads=12, mlp_ratio=4, patch=16, img=224
                 text_hidden=text_hidden, vocab=vocab, max_pos=max_pos, proj_dim=proj_dim)
 
 
+# small geometry used by the tests: head_dim stays 64 (the attention kernels are specialised for it)
+TINY_DIMS = model_dims(embed_dim=128, depth=2, heads=2, patch=16, img=32, num_frames=4, text_dim=128, text_layers=2,
+                       text_heads=2, text_hidden=256, vocab=120, max_pos=32, proj_dim=32)
+
+
 def state_dict_shapes(dims, video=True, text=True, proj=True):
     """Ordered {key: shape} in the reference's registration order."""
     D, H, P = dims["embed_dim"], dims["mlp_hidden"], dims["patch"]

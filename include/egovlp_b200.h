@@ -56,6 +56,7 @@ typedef struct egovlp_gemm_epilogue {
   float alpha;
   float col_scale;
   int col_scale_ncols;
+  int res_row_mod; /* 0: residual row = m; >0: residual row = m % res_row_mod (broadcast [res_row_mod, ldr] table) */
 } egovlp_gemm_epilogue;
 
 int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
@@ -71,13 +72,13 @@ int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B
 int egovlp_layernorm_fwd(const float* x, long long ldx, const float* add, float* sum_out, const float* gamma,
                          const float* beta, void* y_bf16, float* y_f32, float* mean, float* rstd, int rows, int D,
                          float eps, void* stream);
-/* Backward.  dx = LNbwd(dy) [+ add1] [+ add2]  (fp32 [rows, D], row stride D), optionally also stored as bf16
- * (dx_bf16) for use as a GEMM operand.  add1/add2 carry the residual-stream gradients that bypass the LN
+/* Backward.  dx = LNbwd(dy) [+ add1] [+ add2]  (fp32 [rows, D], row stride lddx), optionally also stored as bf16
+ * (dx_bf16, row stride D) for use as a GEMM operand.  add1/add2 carry the residual-stream gradients that bypass the LN
  * (SpaceTimeBlock: dsr = dy + LN2bwd, dx = dsr + dtr + LN3bwd).  dgamma/dbeta (fp32 [D]) are ACCUMULATED
  * with atomicAdd -- zero them first for a plain gradient; either may be NULL. */
 int egovlp_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
                          const float* mean, const float* rstd, const float* add1, const float* add2, float* dx,
-                         void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream);
+                         long long lddx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Divided space-time attention core of VarAttention.forward (model/video_transformer.py:104-133) and its
@@ -97,6 +98,75 @@ int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, float* cls_p
                             int mode, void* stream);
 int egovlp_divided_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                             float* dcls_ws, int B, int T, int N, int H, int mode, float q_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Video patch-embedding front end (model/video_transformer.py:72-77, 304-321).
+ *   egovlp_patch_im2col: video fp32 [B,T,C,H,W] -> patches bf16 [B*S, C*P*P] (row b*S+1+t*N+n, CLS rows zero),
+ *     the A operand of the conv-as-GEMM against patch_embed.proj.weight viewed [D, C*P*P].
+ *   egovlp_video_pos_table: table fp32 [S, D] added by that GEMM's epilogue (res_row_mod = S):
+ *     row 0 = cls_token + pos_embed[0] - conv_bias, row 1+t*N+n = pos_embed[1+n] + temporal_embed[t].
+ *   egovlp_video_embed_bwd: from dx fp32 [B,S,D] ACCUMULATE dcls[D], dpos[(1+N),D], dtemporal[T,D] (first T rows)
+ *     and the conv bias gradient dbias[D]; tmp_SD is an fp32 workspace of S*D floats.
+ */
+int egovlp_patch_im2col(const float* video, void* patches_bf16, int B, int T, int C, int H, int W, int P, void* stream);
+int egovlp_video_pos_table(const float* cls_token, const float* pos_embed, const float* temporal_embed,
+                           const float* conv_bias, float* table, int T, int N, int D, void* stream);
+int egovlp_video_embed_bwd(const float* dx, float* tmp_SD, float* dcls, float* dpos, float* dtemporal, float* dbias,
+                           int B, int T, int N, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text tower pieces (DistilBERT; call sites model/model.py:117-138).  ids / attention_mask are int64 as the
+ * HuggingFace tokenizer returns them.  Head dim 64; L <= 128.
+ *   text_embed_fwd : out fp32 [B*L, D] = word_emb[ids] + pos_emb[l]   (LayerNorm follows via egovlp_layernorm_fwd)
+ *   text_embed_bwd : dword[ids] += dsum, dpos[l] += dsum  (atomic accumulate)
+ *   text_attn_fwd  : out bf16 [B*L, D] = softmax(q k^T + key-padding mask) v per (b, head); qkv bf16 [B*L, 3D],
+ *                    q pre-scaled by 64^-0.5
+ *   text_attn_bwd  : dqkv bf16 [B*L, 3D]  (dq multiplied by q_scale)
+ *   relu_rows      : out bf16 [rows, D] = relu(x[r*row_stride + :D]) (CLS -> ReLU of txt_proj, model/model.py:73-75)
+ */
+int egovlp_text_embed_fwd(const long long* input_ids, const float* word_emb, const float* pos_emb, float* out, int B,
+                          int L, int D, void* stream);
+int egovlp_text_embed_bwd(const long long* input_ids, const float* dsum, float* dword, float* dpos, int B, int L, int D,
+                          void* stream);
+int egovlp_text_attn_fwd(const void* qkv, const long long* attention_mask, void* out, int B, int L, int H, void* stream);
+int egovlp_text_attn_bwd(const void* qkv, const long long* attention_mask, const void* dout, void* dqkv, int B, int L,
+                         int H, float q_scale, void* stream);
+int egovlp_relu_rows_fwd(const float* x, long long row_stride, void* out_bf16, int rows, int D, void* stream);
+int egovlp_relu_rows_bwd(const float* x, long long row_stride, const float* dh, float* dx, int rows, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Similarity and losses, fp32 (model/model.py:189-197 sim_matrix; model/loss.py EgoNCE :34-53,
+ * NormSoftmaxLoss :13-25, MaxMarginRankingLoss :63-90; run/test_epic.py:137-143 dual softmax;
+ * trainer/trainer_egoclip.py:204-215 + model/metric.py:227 EgoMCQ scoring).
+ *   rownorm_fwd: an = a / max(||a||, eps) per row, norm[rows] saved;  rownorm_bwd: its backward.
+ *   sgemm_f32 : C[m,n] = alpha * sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] + beta*C  (small fp32 products:
+ *               sim = an bn^T, d an = dX bn, d bn = dX^T an)
+ *   pack_multihot / mask_from_bits: positives mask uint8 [G,G] from multi-hot verb/noun vectors
+ *               (mode 0 identity, 1 verb&noun, 2 noun, 3 verb; diagonal always set) -- equals the reference's
+ *               (sim_v*sim_n + I) > 0 for 0/1 tags;  mask_from_sims: the reference's float formulation itself.
+ *   nce_fwd   : stats fp32 [4G] (row/col log-sum-exp over all / over positives of x*inv_temp), loss scalar
+ *   nce_bwd   : dx fp32 [G,G] = gscale[0] * dloss/dx   (gscale device pointer or NULL for 1)
+ *   maxmargin_fwd/bwd, dual_softmax (in: sim [rows, cols] -> out), egomcq_score (scores [Q,K], pred int64 [Q],
+ *               ties -> lowest index).
+ */
+int egovlp_rownorm_fwd(const float* a, float* an, float* norm, int rows, int C, float eps, void* stream);
+int egovlp_rownorm_bwd(const float* dan, const float* an, const float* norm, float* da, int rows, int C, float eps,
+                       void* stream);
+int egovlp_sgemm_f32(const float* A, long long sam, long long sak, const float* B, long long sbn, long long sbk,
+                     float* C, long long ldc, int M, int N, int K, float alpha, float beta, void* stream);
+int egovlp_pack_multihot(const float* v, uint32_t* bits, int G, int C, void* stream);
+int egovlp_mask_from_bits(const uint32_t* vbits, int n_verb, const uint32_t* nbits, int n_noun, uint8_t* mask, int G,
+                          int mode, void* stream);
+int egovlp_mask_from_sims(const float* sim_v, const float* sim_n, uint8_t* mask, int G, int mode, void* stream);
+int egovlp_nce_fwd(const float* x, const uint8_t* mask, int G, float inv_temp, float* stats, float* loss, void* stream);
+int egovlp_nce_bwd(const float* x, const uint8_t* mask, const float* stats, int G, float inv_temp, const float* gscale,
+                   float* dx, void* stream);
+int egovlp_maxmargin_fwd(const float* x, int G, float margin, int fix_norm, float* loss, void* stream);
+int egovlp_maxmargin_bwd(const float* x, int G, float margin, int fix_norm, const float* gscale, float* dx,
+                         void* stream);
+int egovlp_dual_softmax(const float* sim, float* out, int rows, int cols, float temp, void* stream);
+int egovlp_egomcq_score(const float* text, const float* video, float* scores, long long* pred, int Q, int K, int C,
+                        float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers on the path.

@@ -17,8 +17,7 @@ from oracle import ref_shim  # noqa: E402
 from egovlp_b200 import synthetic as syn  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
-TINY = syn.model_dims(embed_dim=64, depth=2, heads=4, patch=16, img=32, num_frames=4,
-                      text_dim=64, text_layers=2, text_heads=4, text_hidden=128, vocab=120, max_pos=32, proj_dim=32)
+TINY = syn.TINY_DIMS
 
 
 def npz(name, **arrs):
@@ -31,7 +30,7 @@ def npz(name, **arrs):
 def video_tiny():
     _, vt, _ = ref_shim.modules()
     sd = syn.seeded_state_dict(TINY, seed=3, text=False, proj=False)
-    net = vt.SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=64, depth=2, num_heads=4, num_frames=4,
+    net = vt.SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_frames=4,
                                   time_init="zeros", num_classes=0)
     net.pre_logits = torch.nn.Identity()
     missing = net.load_state_dict({k[len("video_model."):]: v for k, v in sd.items()}, strict=True)
@@ -42,8 +41,7 @@ def video_tiny():
     probe = torch.randn(out.shape, generator=torch.Generator().manual_seed(9))
     (out * probe).sum().backward()
     grads = {n: p.grad for n, p in net.named_parameters()}
-    npz("video_tiny.npz", video=video, out=out, probe=probe,
-        **{"w:" + k: v for k, v in sd.items()},
+    npz("video_tiny.npz", video=video, out=out, probe=probe, seed=3,
         **{"g:video_model." + n: g for n, g in grads.items() if g is not None and (
             "blocks.1.timeattn.qkv" in n or "blocks.0.attn.proj.weight" in n or "blocks.0.mlp.fc1.bias" in n
             or n in ("cls_token", "temporal_embed", "pos_embed", "patch_embed.proj.weight", "norm.weight",
@@ -53,14 +51,13 @@ def video_tiny():
 def distilbert_tiny():
     from transformers import DistilBertConfig, DistilBertModel
     sd = syn.seeded_state_dict(TINY, seed=4, video=False, proj=False)
-    cfg = DistilBertConfig(vocab_size=120, dim=64, n_layers=2, n_heads=4, hidden_dim=128, max_position_embeddings=32,
+    cfg = DistilBertConfig(vocab_size=120, dim=128, n_layers=2, n_heads=2, hidden_dim=256, max_position_embeddings=32,
                            dropout=0.0, attention_dropout=0.0)
     net = DistilBertModel(cfg).eval()
     print("distilbert_tiny load:", net.load_state_dict({k[len("text_model."):]: v for k, v in sd.items()}, strict=True))
     text = syn.synthetic_text(5, 9, seed=1, ragged=True, vocab=120)
     out = net(**text).last_hidden_state
-    npz("distilbert_tiny.npz", input_ids=text["input_ids"], attention_mask=text["attention_mask"], out=out,
-        **{"w:" + k: v for k, v in sd.items()})
+    npz("distilbert_tiny.npz", input_ids=text["input_ids"], attention_mask=text["attention_mask"], out=out, seed=4)
 
 
 def losses():

@@ -13,8 +13,9 @@ def close(a, b, rtol=2e-5, atol=2e-6):
 
 def test_video_tower_tiny_forward_and_grads():
     g = load_golden("video_tiny.npz")
-    p = {k: v.clone().requires_grad_(True) for k, v in weights_of(g).items()}
-    out = rp.video_tower(g["video"], p, heads=4)
+    sd = syn.seeded_state_dict(syn.TINY_DIMS, seed=int(g["seed"]), text=False, proj=False)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = rp.video_tower(g["video"], p, heads=2)
     close(out, g["out"], rtol=1e-4, atol=1e-5)
     (out * g["probe"]).sum().backward()
     checked = 0
@@ -27,7 +28,8 @@ def test_video_tower_tiny_forward_and_grads():
 
 def test_distilbert_tiny():
     g = load_golden("distilbert_tiny.npz")
-    out = rp.distilbert_forward(g["input_ids"], g["attention_mask"], weights_of(g), heads=4)
+    sd = syn.seeded_state_dict(syn.TINY_DIMS, seed=int(g["seed"]), video=False, proj=False)
+    out = rp.distilbert_forward(g["input_ids"], g["attention_mask"], sd, heads=2)
     close(out, g["out"], rtol=1e-4, atol=1e-5)
 
 
