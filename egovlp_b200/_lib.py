@@ -31,9 +31,26 @@ def lib():
     return _lib
 
 
+# kernels launched per C-ABI call (memsets excluded) -- bench.py reports the count as `gpu_launches`
+_KERNELS_PER_CALL = {"egovlp_divided_attn_fwd": 2, "egovlp_divided_attn_bwd": 2, "egovlp_video_embed_bwd": 2,
+                     "egovlp_nce_fwd": 2, "egovlp_dual_softmax": 2}
+_launches = 0
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def launch_count():
+    return _launches
+
+
 def call(name, *args):
+    global _launches
     fn = getattr(lib(), name)
     rc = fn(*args)
+    _launches += _KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise EgovlpError(f"{name} failed ({rc}): {lib().egovlp_last_error().decode()}")
 

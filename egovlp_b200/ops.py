@@ -21,6 +21,21 @@ def _chk(t, dtype, name):
     assert t.is_cuda and t.dtype == dtype, f"{name}: expected cuda {dtype}, got {t.device} {t.dtype}"
 
 
+_gemm_prof = None
+
+
+def profile_gemm(enable):
+    """bench.py's live roofline probe: CUDA events (on the launching stream) around every tcgen05 GEMM launch.
+    profile_gemm(True) starts recording; profile_gemm(False) returns (flops, milliseconds, launches)."""
+    global _gemm_prof
+    if enable:
+        _gemm_prof = []
+        return None
+    rec, _gemm_prof = _gemm_prof or [], None
+    torch.cuda.synchronize()
+    return sum(r[0] for r in rec), sum(r[1].elapsed_time(r[2]) for r in rec), len(rec)
+
+
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, out2=None, act=0, alpha=1.0,
          col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0):
     """out = epi(A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, last-dim contiguous.
@@ -57,8 +72,14 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
         e.out_mode = 0 if out.dtype == BF16 else 1
     e.act, e.alpha, e.col_scale, e.col_scale_ncols = act, alpha, col_scale, col_scale_ncols
     e.res_row_mod = res_row_mod
+    if _gemm_prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     call("egovlp_gemm_bf16", _ptr(a), int(a_mn), C.c_longlong(a.stride(0)), _ptr(b), int(b_mn),
          C.c_longlong(b.stride(0)), M, N, K, C.byref(e), split_k, _stream())
+    if _gemm_prof is not None:
+        e1.record()
+        _gemm_prof.append((2.0 * M * N * K, e0, e1))
     return out
 
 

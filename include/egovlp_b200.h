@@ -176,6 +176,26 @@ int egovlp_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void*
 /* out[n] += sum_m dy[m, n]  (bias gradients).  dy bf16 or fp32 [M, N] row stride ld. */
 int egovlp_colsum_accum(const void* dy, int dy_is_fp32, long long ld, float* out, int M, int N, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW, HuggingFace transformers.AdamW semantics (run/train_egoclip.py:72-73,
+ * configs/pt/egoclip.json:49-54): m,v update; p -= step_size * m / (sqrt(v) + eps) with
+ * step_size = lr * sqrt(1-b2^t)/(1-b1^t) (computed by the host); then p -= lr * wd * p.
+ * tensors_dev: device array of descriptors; chunk_tensor_dev / chunk_offset_dev: for every CTA the tensor index
+ * and the chunk index (egovlp_adamw_chunk_elems() elements per chunk) it updates.  grad_scale_dev: optional
+ * device scalar multiplied into every gradient (e.g. 1/world for a summed all-reduce), or NULL.
+ */
+typedef struct egovlp_adamw_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+} egovlp_adamw_tensor;
+int egovlp_adamw_chunk_elems(void);
+int egovlp_adamw_multi(const egovlp_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_offset_dev,
+                       int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, float step_size,
+                       const float* grad_scale_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

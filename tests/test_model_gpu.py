@@ -131,7 +131,7 @@ def test_text_tower_tiny_vs_oracle():
     (cls * probe.cuda()).sum().backward()
     for k in order:
         ref = p_cpu[k].grad
-        if ref is None or ref.norm() < 1e-7:
+        if ref is None or k.endswith("k_lin.bias"):      # k bias gradient is analytically zero (softmax shift invariance)
             continue
         assert cos(p_gpu[k].grad, ref) > 0.995, (k, cos(p_gpu[k].grad, ref))
 
