@@ -42,6 +42,25 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """CPU threads this process may really use: affinity mask capped by the cgroup CPU quota (os.cpu_count() reports
+    the host's cores even inside a CPU-limited container, and oversubscribing torch threads is catastrophic)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, min(n, 32))   # beyond ~32 threads the fp32 eager path at this size scales negatively
+
+
 class ClockSampler:
     """nvidia-smi SM clock / throttle reasons sampled during the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -84,7 +103,7 @@ def cpu_reference_step_rate(T, L, steps, warmup, batch=2, seed=0):
     `batch` clips of T frames, fwd + bwd + AdamW.  Returns clips/s and a description."""
     from oracle import reference_port as rp
     from egovlp_b200 import synthetic as syn
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     torch.set_num_threads(cores)
     dims = syn.model_dims(num_frames=max(T, 4))
     params = {k: v.requires_grad_(True) for k, v in syn.seeded_state_dict(dims, seed=seed).items()}
@@ -103,10 +122,13 @@ def cpu_reference_step_rate(T, L, steps, warmup, batch=2, seed=0):
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    done = 0
+    while done < steps and (done == 0 or time.perf_counter() - t0 < 45.0):     # bounded: ~10-45 s of CPU work
         step()
+        done += 1
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, cores, f"oracle port, fp32, {batch} clips x {T}f x 224^2 + {L} tokens, fwd+bwd+AdamW, {steps} steps"
+    return (batch * done / dt, dt / done, cores,
+            f"oracle port, fp32, {batch} clips x {T}f x 224^2 + {L} tokens, fwd+bwd+AdamW, {done} timed steps on {cores} threads")
 
 
 def run_reference(args):

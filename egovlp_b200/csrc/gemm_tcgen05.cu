@@ -48,11 +48,55 @@ struct Cfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;
+  static constexpr int SMEM_BYTES =
+      STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA per element instead of erff's ~30
+// instructions -- the GELU epilogue has to finish inside the 6144-cycle MMA time of a K=768 tile.
+__device__ __forceinline__ float erf_abs_fast(float z, float e) {   // z >= 0, e = exp(-z*z)
+  const float t = 1.f / (1.f + 0.3275911f * z);
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return 1.f - poly * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float e = __expf(-0.5f * x * x);
+  const float er = copysignf(erf_abs_fast(fabsf(x) * 0.70710678118654752f, e), x);
+  return 0.5f * x * (1.f + er);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float e = __expf(-0.5f * x * x);
+  const float er = copysignf(erf_abs_fast(fabsf(x) * 0.70710678118654752f, e), x);
+  return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
+}
+
+// Epilogue staging (warp-private, 32 rows x 128 B).  bf16: a row's 32 values = 4 x 16B chunks placed at slot
+// (c ^ ((r>>1)&3)) + 4*(r&1) so that both the row-owner writes and the 4-lanes-per-row reads are conflict-free.
+__device__ __forceinline__ void stage_bf16_rows(uint32_t stg, int lane, const float (&v)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t a = stg + lane * 128 + ((((c ^ ((lane >> 1) & 3)) + 4 * (lane & 1))) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * c], v[8 * c + 1])),
+                 "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
+                 "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7])));
+  }
+}
+__device__ __forceinline__ void store_bf16_coalesced(const uint8_t* stg_gen, int lane, bf16* out, long long ldo, int row0,
+                                                     int n0, int M) {
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = 8 * i + (lane >> 2), grow = row0 + rl;
+    if (grow < M) {
+      const uint4 x = *reinterpret_cast<const uint4*>(stg_gen + rl * 128 + (((c ^ ((rl >> 1) & 3)) + 4 * (rl & 1)) << 4));
+      *reinterpret_cast<uint4*>(out + (long long)grow * ldo + n0 + c * 8) = x;
+    }
+  }
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -65,7 +109,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bars = sB + STAGES * C::B_STAGE_BYTES;
+  const uint32_t epi_stage = sB + STAGES * C::B_STAGE_BYTES;
+  const uint32_t bars = epi_stage + C::EPI_STAGE_BYTES;
   const uint32_t full_bar = bars;                    // STAGES x 8B
   const uint32_t empty_bar = bars + 8 * STAGES;      // STAGES x 8B
   const uint32_t tfull_bar = bars + 16 * STAGES;     // 2 x 8B
@@ -174,6 +219,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int q = warp & 3;       // TMEM lane quarter this warp may read
     const int half = e >> 2;      // which half of the BLOCK_N columns
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const uint32_t stg = epi_stage + e * 4096;
+    const uint8_t* stg_gen = smem_gen + (stg - smem_base);
     int it = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
       const int split = unit / num_tiles, tile = unit - split * num_tiles;
@@ -182,9 +229,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const bool row_ok = row < M;
+      const int row0 = m_blk * BLOCK_M + q * 32;     // first of this warp's 32 rows
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
+      // Each chunk: TMEM -> registers in row-owner layout (lane = row, 32 consecutive columns) -> per-column math
+      // -> warp-private swizzled smem transpose -> coalesced layout (a row's 64/128 B handled by 4/8 adjacent lanes)
+      // -> per-element operands (residual, aux) and full-sector global stores.
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
         uint32_t r[32];
@@ -197,7 +246,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
         }
         const int n0 = n_blk * BLOCK_N + half * COLS_PER_WARP + c;
-        if (!row_ok || n0 >= N) continue;
+        if (n0 >= N) continue;     // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
@@ -214,52 +263,58 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) v[j] *= ep.col_scale;
         }
         if (ep.out2) {
-          uint4* o = reinterpret_cast<uint4*>(ep.out2 + (long long)row * ep.ldo2 + n0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          stage_bf16_rows(stg, lane, v);
+          __syncwarp();
+          store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
+          __syncwarp();
         }
         if (ep.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        } else if (ep.act == 2) {
-          const uint4* a4 = reinterpret_cast<const uint4*>(ep.aux + (long long)row * ep.ldaux + n0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 a = __ldg(a4 + j);
-            const float2 p0 = unpack_bf16x2(a.x), p1 = unpack_bf16x2(a.y), p2 = unpack_bf16x2(a.z),
-                         p3 = unpack_bf16x2(a.w);
-            v[8 * j] *= gelu_erf_grad(p0.x); v[8 * j + 1] *= gelu_erf_grad(p0.y);
-            v[8 * j + 2] *= gelu_erf_grad(p1.x); v[8 * j + 3] *= gelu_erf_grad(p1.y);
-            v[8 * j + 4] *= gelu_erf_grad(p2.x); v[8 * j + 5] *= gelu_erf_grad(p2.y);
-            v[8 * j + 6] *= gelu_erf_grad(p3.x); v[8 * j + 7] *= gelu_erf_grad(p3.y);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
-        if (ep.residual) {
-          const int rrow = ep.res_row_mod ? row % ep.res_row_mod : row;
-          const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + n0);
+        const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2;
+        if (!wide) {
+          stage_bf16_rows(stg, lane, v);
+          __syncwarp();
+          store_bf16_coalesced(stg_gen, lane, reinterpret_cast<bf16*>(ep.out), ep.ldo, row0, n0, M);
+        } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(r4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            const uint32_t a = stg + lane * 128 + ((j ^ (lane & 7)) << 4);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3]));
+          }
+          __syncwarp();
+          const int c4 = lane & 7;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = 4 * i + (lane >> 3), grow = row0 + rl;
+            if (grow < M) {
+              float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+              const int col = n0 + c4 * 4;
+              if (ep.act == 2) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
+                const float2 p0 = unpack_bf16x2(a.x), p1 = unpack_bf16x2(a.y);
+                x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
+                x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
+              }
+              if (ep.residual) {
+                const int rrow = ep.res_row_mod ? grow % ep.res_row_mod : grow;
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + col));
+                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+              }
+              if (ep.out_mode == 0) {
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (long long)grow * ep.ldo + col) =
+                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+              } else if (ep.out_mode == 1) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col) = x;
+              } else {
+                red_add_v4(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col, x.x, x.y, x.z, x.w);
+              }
+            }
           }
         }
-        if (ep.out_mode == 0) {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(ep.out) + (long long)row * ep.ldo + n0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        } else if (ep.out_mode == 1) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + n0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-          float* o = reinterpret_cast<float*>(ep.out) + (long long)row * ep.ldo + n0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) red_add_v4(o + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
+        __syncwarp();   // staging buffer is reused by the next chunk
       }
     }
   }

@@ -191,3 +191,56 @@ def test_egomcq_argmax_bit_exact_at_scale():
     s_ref, pred_ref = rp.egomcq_predict(t, v)
     assert torch.equal(pred.cpu(), pred_ref)
     torch.testing.assert_close(s.cpu(), s_ref, rtol=1e-5, atol=1e-6)
+
+
+def test_fused_adamw_matches_hf_semantics():
+    """transformers.AdamW (4.x) update rule restated in torch vs the fused multi-tensor kernel, 3 steps."""
+    from egovlp_b200.optim import AdamW
+    g = torch.Generator().manual_seed(3)
+    shapes = [(768, 768), (3072,), (1, 17, 768), (5,), (30522, 8)]
+    ps = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone() for p in ps]
+    m = [torch.zeros_like(p) for p in ref]
+    v = [torch.zeros_like(p) for p in ref]
+    lr, b1, b2, eps, wd = 3e-3, 0.9, 0.999, 1e-6, 0.01
+    opt = AdamW(ps, lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd)
+    for step in range(1, 4):
+        grads = [torch.randn(s, generator=g).cuda() for s in shapes]
+        for p, gr in zip(ps, grads):
+            p.grad = gr.clone()
+        ver = ps[0]._version
+        opt.step()
+        assert ps[0]._version > ver
+        for i, gr in enumerate(grads):
+            m[i].mul_(b1).add_(gr, alpha=1 - b1)
+            v[i].mul_(b2).addcmul_(gr, gr, value=1 - b2)
+            step_size = lr * (1 - b2 ** step) ** 0.5 / (1 - b1 ** step)
+            ref[i].addcdiv_(m[i], v[i].sqrt().add_(eps), value=-step_size)
+            ref[i].add_(ref[i], alpha=-lr * wd)
+        for p, r in zip(ps, ref):
+            torch.testing.assert_close(p.detach(), r, rtol=2e-5, atol=2e-6)
+
+
+def test_training_steps_reduce_loss_tiny():
+    """A few fused steps (model -> packed gather (world 1) -> EgoNCE.fused -> backward -> AdamW) on the tiny tower."""
+    from egovlp_b200 import synthetic as syn
+    from egovlp_b200.model.loss import EgoNCE
+    from egovlp_b200.model.video_transformer import SpaceTimeTransformer
+    from egovlp_b200.optim import AdamW
+    sd = syn.seeded_state_dict(syn.TINY_DIMS, seed=11, text=False, proj=False)
+    net = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_frames=4,
+                               time_init="zeros", num_classes=0)
+    net.load_state_dict({k[len("video_model."):]: v for k, v in sd.items()})
+    net.cuda()
+    opt = AdamW(net.parameters(), lr=1e-3)
+    video = syn.synthetic_video(8, 4, seed=2, img=32).cuda()
+    text = torch.randn(8, 128, generator=torch.Generator().manual_seed(4)).cuda()
+    verb, noun = [t.cuda() for t in syn.synthetic_tags(8, seed=3)]
+    losses = []
+    for _ in range(8):
+        opt.zero_grad(set_to_none=True)
+        loss = EgoNCE().fused(text, net(video), verb, noun)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0] - 0.05, losses
