@@ -123,6 +123,28 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
   __syncwarp();
 }
 
+// Same, straight from the fragments (each quad writes 16 contiguous bytes of a row): used by the backward, whose
+// four resident tiles leave no room for staging when two CTAs share an SM.
+__device__ __forceinline__ void store_frag_rows_bf16(const float (&acc)[8][4], float s, bf16* dst, long long ld, int col0,
+                                                     const Geom& G, int b, int g, int r0, int lane) {
+  const int gq = lane >> 2, t = lane & 3;
+  const int tok0 = row_token(G, g, r0 + gq), tok1 = row_token(G, g, r0 + gq + 8);
+  bf16* p0 = dst + ((long long)b * G.S + tok0) * ld + col0 + 2 * t;
+  bf16* p1 = dst + ((long long)b * G.S + tok1) * ld + col0 + 2 * t;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (tok0 > 0) *reinterpret_cast<uint32_t*>(p0 + 8 * j) = pack_bf16x2(acc[j][0] * s, acc[j][1] * s);
+    if (tok1 > 0) *reinterpret_cast<uint32_t*>(p1 + 8 * j) = pack_bf16x2(acc[j][2] * s, acc[j][3] * s);
+  }
+}
+
+// A 16-row tile is "uniform" when all its rows are valid patch rows of one group id; an 8-wide tile on the other
+// side is then fully attendable (no masking, no gid lookups) iff its first and last rows carry that same id.
+__device__ __forceinline__ int tile_uniform_gid(const short* gid, int r0) {
+  const int a = gid[r0], b = gid[r0 + 15];
+  return (a >= 0 && a == b) ? a : -1;
+}
+
 __device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int& g) {
   g = blockIdx.x % G.G;
   const int bh = blockIdx.x / G.G;
@@ -142,7 +164,7 @@ __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_
   sm.dout = sm.v + tile_bytes;
   uint32_t off = (BWD ? 4 : 3) * tile_bytes;
   sm.stage = smem_base + off;
-  off += nwarps * 16 * ROW_BYTES;
+  if (!BWD) off += nwarps * 16 * ROW_BYTES;
   sm.lse = reinterpret_cast<float*>(smem_gen + off);
   off += G.NPAD * 4;
   sm.delta = reinterpret_cast<float*>(smem_gen + off);
@@ -219,6 +241,7 @@ divided_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* 
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) load_a_frag(sm.q, r0, kk, lane, qf[kk]);
     const int gid0 = sm.gid[r0 + gq], gid1 = sm.gid[r0 + gq + 8];
+    const int ugid = tile_uniform_gid(sm.gid, r0);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     float o[8][4];
 #pragma unroll
@@ -242,17 +265,20 @@ divided_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* 
           }
         }
       }
-      // mask
+      // mask (skipped for tiles that are fully attendable by every row of this tile)
       float cm0 = -INFINITY, cm1 = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int col = (c0 + j) * 8 + 2 * t;
         const bool inb = (c0 + j) < NT;
-        const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
-        s[j][0] = pair_valid(gid0, k0, first_group) ? s[j][0] : -INFINITY;
-        s[j][1] = pair_valid(gid0, k1, first_group) ? s[j][1] : -INFINITY;
-        s[j][2] = pair_valid(gid1, k0, first_group) ? s[j][2] : -INFINITY;
-        s[j][3] = pair_valid(gid1, k1, first_group) ? s[j][3] : -INFINITY;
+        const bool fast = inb && ugid >= 0 && sm.gid[(c0 + j) * 8] == ugid && sm.gid[(c0 + j) * 8 + 7] == ugid;
+        if (!fast) {
+          const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
+          s[j][0] = pair_valid(gid0, k0, first_group) ? s[j][0] : -INFINITY;
+          s[j][1] = pair_valid(gid0, k1, first_group) ? s[j][1] : -INFINITY;
+          s[j][2] = pair_valid(gid1, k0, first_group) ? s[j][2] : -INFINITY;
+          s[j][3] = pair_valid(gid1, k1, first_group) ? s[j][3] : -INFINITY;
+        }
         cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
         cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
       }
@@ -358,8 +384,6 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
   const int gq = lane >> 2, t = lane & 3;
   const bool first_group = (g == 0);
   const int NT = G.NPAD / 8;
-  const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
-  uint8_t* stage_gen = smem_gen + (stage - smem_base);
 
   // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row
   for (int r = warp * 4 + (lane >> 3); r < G.NPAD; r += NWARPS * 4) {
@@ -388,10 +412,8 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const int r0 = rt * 16;
     int lo, hi;
     tile_window(G, r0, lo, hi);
-    uint32_t qf[4][4], df[4][4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) { load_a_frag(sm.q, r0, kk, lane, qf[kk]); load_a_frag(sm.dout, r0, kk, lane, df[kk]); }
     const int gid0 = sm.gid[r0 + gq], gid1 = sm.gid[r0 + gq + 8];
+    const int ugid = tile_uniform_gid(sm.gid, r0);
     const float ls0 = sm.lse[r0 + gq], ls1 = sm.lse[r0 + gq + 8], de0 = sm.delta[r0 + gq], de1 = sm.delta[r0 + gq + 8];
     float dq[8][4];
 #pragma unroll
@@ -407,13 +429,15 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         if (c0 + 2 * p < NT && span_active(G, lo, hi, n0, 16)) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            uint32_t bf[4];
+            uint32_t af[4], bf[4];     // A fragments re-read per use: registers are what limits CTAs per SM here
+            load_a_frag(sm.q, r0, kk, lane, af);
             load_b_frag_nk(sm.k, n0, kk, lane, bf);
-            mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
-            mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
+            mma_bf16(s[2 * p], af, bf[0], bf[1]);
+            mma_bf16(s[2 * p + 1], af, bf[2], bf[3]);
+            load_a_frag(sm.dout, r0, kk, lane, af);
             load_b_frag_nk(sm.v, n0, kk, lane, bf);
-            mma_bf16(dp[2 * p], df[kk], bf[0], bf[1]);
-            mma_bf16(dp[2 * p + 1], df[kk], bf[2], bf[3]);
+            mma_bf16(dp[2 * p], af, bf[0], bf[1]);
+            mma_bf16(dp[2 * p + 1], af, bf[2], bf[3]);
           }
         }
       }
@@ -422,11 +446,17 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int j = 0; j < 4; ++j) {
         const int col = (c0 + j) * 8 + 2 * t;
         const bool inb = (c0 + j) < NT;
-        const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
-        const float p0 = pair_valid(gid0, k0, first_group) ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
-        const float p1 = pair_valid(gid0, k1, first_group) ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
-        const float p2 = pair_valid(gid1, k0, first_group) ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
-        const float p3 = pair_valid(gid1, k1, first_group) ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
+        const bool fast = inb && ugid >= 0 && sm.gid[(c0 + j) * 8] == ugid && sm.gid[(c0 + j) * 8 + 7] == ugid;
+        bool v0 = true, v1 = true, v2 = true, v3 = true;
+        if (!fast) {
+          const int k0 = inb ? sm.gid[col] : -1, k1 = inb ? sm.gid[col + 1] : -1;
+          v0 = pair_valid(gid0, k0, first_group); v1 = pair_valid(gid0, k1, first_group);
+          v2 = pair_valid(gid1, k0, first_group); v3 = pair_valid(gid1, k1, first_group);
+        }
+        const float p0 = v0 ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
+        const float p1 = v1 ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
+        const float p2 = v2 ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
+        const float p3 = v3 ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
         dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
         dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
       }
@@ -457,7 +487,7 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
     }
-    store_rows_bf16(dq, q_scale, q_scale, stage, stage_gen, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane, true);
+    store_frag_rows_bf16(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane);
   }
 
   // phase 2: per 16 keys -> dK, dV
@@ -465,10 +495,8 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
     const int k0r = kt * 16;
     int lo, hi;
     tile_window(G, k0r, lo, hi);
-    uint32_t kf[4][4], vf[4][4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) { load_a_frag(sm.k, k0r, kk, lane, kf[kk]); load_a_frag(sm.v, k0r, kk, lane, vf[kk]); }
     const int gid0 = sm.gid[k0r + gq], gid1 = sm.gid[k0r + gq + 8];
+    const int ugid = tile_uniform_gid(sm.gid, k0r);
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
@@ -483,13 +511,15 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         if (c0 + 2 * p < NT && span_active(G, lo, hi, n0, 16)) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            uint32_t bf[4];
+            uint32_t af[4], bf[4];
+            load_a_frag(sm.k, k0r, kk, lane, af);
             load_b_frag_nk(sm.q, n0, kk, lane, bf);
-            mma_bf16(st[2 * p], kf[kk], bf[0], bf[1]);
-            mma_bf16(st[2 * p + 1], kf[kk], bf[2], bf[3]);
+            mma_bf16(st[2 * p], af, bf[0], bf[1]);
+            mma_bf16(st[2 * p + 1], af, bf[2], bf[3]);
+            load_a_frag(sm.v, k0r, kk, lane, af);
             load_b_frag_nk(sm.dout, n0, kk, lane, bf);
-            mma_bf16(dpt[2 * p], vf[kk], bf[0], bf[1]);
-            mma_bf16(dpt[2 * p + 1], vf[kk], bf[2], bf[3]);
+            mma_bf16(dpt[2 * p], af, bf[0], bf[1]);
+            mma_bf16(dpt[2 * p + 1], af, bf[2], bf[3]);
           }
         }
       }
@@ -498,13 +528,19 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
       for (int j = 0; j < 4; ++j) {
         const int col = (c0 + j) * 8 + 2 * t;       // query index
         const bool inb = (c0 + j) < NT;
-        const int q0 = inb ? sm.gid[col] : -1, q1 = inb ? sm.gid[col + 1] : -1;
+        const bool fast = inb && ugid >= 0 && sm.gid[(c0 + j) * 8] == ugid && sm.gid[(c0 + j) * 8 + 7] == ugid;
+        bool v0 = true, v1 = true, v2 = true, v3 = true;
+        if (!fast) {
+          const int q0 = inb ? sm.gid[col] : -1, q1 = inb ? sm.gid[col + 1] : -1;
+          v0 = pair_valid(q0, gid0, first_group); v1 = pair_valid(q1, gid0, first_group);
+          v2 = pair_valid(q0, gid1, first_group); v3 = pair_valid(q1, gid1, first_group);
+        }
         const float lq0 = inb ? sm.lse[col] : 0.f, lq1 = inb ? sm.lse[col + 1] : 0.f;
         const float dq0 = inb ? sm.delta[col] : 0.f, dq1 = inb ? sm.delta[col + 1] : 0.f;
-        const float p0 = pair_valid(q0, gid0, first_group) ? exp2f(st[j][0] * LOG2E - lq0) : 0.f;
-        const float p1 = pair_valid(q1, gid0, first_group) ? exp2f(st[j][1] * LOG2E - lq1) : 0.f;
-        const float p2 = pair_valid(q0, gid1, first_group) ? exp2f(st[j][2] * LOG2E - lq0) : 0.f;
-        const float p3 = pair_valid(q1, gid1, first_group) ? exp2f(st[j][3] * LOG2E - lq1) : 0.f;
+        const float p0 = v0 ? exp2f(st[j][0] * LOG2E - lq0) : 0.f;
+        const float p1 = v1 ? exp2f(st[j][1] * LOG2E - lq1) : 0.f;
+        const float p2 = v2 ? exp2f(st[j][2] * LOG2E - lq0) : 0.f;
+        const float p3 = v3 ? exp2f(st[j][3] * LOG2E - lq1) : 0.f;
         pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
         pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
         dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq0), p1 * (dpt[j][1] - dq1));
@@ -542,8 +578,8 @@ divided_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid
         }
       }
     }
-    store_rows_bf16(dk, 1.f, 1.f, stage, stage_gen, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane, true);
-    store_rows_bf16(dv, 1.f, 1.f, stage, stage_gen, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane, true);
+    store_frag_rows_bf16(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane);
+    store_frag_rows_bf16(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane);
   }
 }
 
@@ -581,7 +617,7 @@ int make_group_tmap(CUtensorMap* tm, const void* base, const Geom& G, int ncolbl
 }
 
 size_t attn_smem_bytes(const Geom& G, bool bwd, int nwarps) {
-  return (size_t)(bwd ? 4 : 3) * G.NPAD * ROW_BYTES + nwarps * 16 * ROW_BYTES + 2 * G.NPAD * 4 +
+  return (size_t)(bwd ? 4 : 3) * G.NPAD * ROW_BYTES + (bwd ? 0 : nwarps * 16 * ROW_BYTES) + 2 * G.NPAD * 4 +
          ((G.NPAD * 2 + 15) / 16) * 16 + 16 + 1024;
 }
 
@@ -644,9 +680,9 @@ extern "C" int egovlp_divided_attn_bwd(const void* qkv, const void* out, const v
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   EGOVLP_CHECK_CUDA(cudaMemsetAsync(dcls_ws, 0, (size_t)B * H * 3 * HD * sizeof(float), st));
   if (G.NPAD > 128) {   // space: 13 row tiles over 7 warps, 1 CTA / SM (4 tiles of 26 KB), up to 255 registers
-    constexpr int W = 7;
+    constexpr int W = 7;     // 2 CTAs / SM: 4 x 26 KB tiles each, no staging
     const size_t smem = attn_smem_bytes(G, true, W);
-    auto kern = divided_attn_bwd_kernel<W, 1>;
+    auto kern = divided_attn_bwd_kernel<W, 2>;
     EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<B * H * G.G, W * 32, smem, st>>>(tmq, tmd, reinterpret_cast<const bf16*>(qkv),
                                            reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), lse,

@@ -286,23 +286,31 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           __syncwarp();
           const int c4 = lane & 7;
+          const int col = n0 + c4 * 4;
+          // issue every per-element global load of the chunk first (rows clamped, no branches) so that 8 independent
+          // requests per lane are in flight instead of one latency-bound load per iteration
+          float4 resv[8];
+          uint2 auxv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = min(row0 + 4 * i + (lane >> 3), M - 1);
+            if (ep.residual) {
+              const int rrow = ep.res_row_mod ? grow % ep.res_row_mod : grow;
+              resv[i] = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + col));
+            }
+            if (ep.act == 2) auxv[i] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
+          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rl = 4 * i + (lane >> 3), grow = row0 + rl;
+            float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            if (ep.act == 2) {
+              const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
+              x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
+              x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
+            }
+            if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
             if (grow < M) {
-              float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-              const int col = n0 + c4 * 4;
-              if (ep.act == 2) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
-                const float2 p0 = unpack_bf16x2(a.x), p1 = unpack_bf16x2(a.y);
-                x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
-                x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
-              }
-              if (ep.residual) {
-                const int rrow = ep.res_row_mod ? grow % ep.res_row_mod : grow;
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + col));
-                x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
-              }
               if (ep.out_mode == 0) {
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (long long)grow * ep.ldo + col) =
                     make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));

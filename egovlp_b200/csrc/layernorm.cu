@@ -66,7 +66,7 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
 }
 
 template <int NV>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)   // <=128 registers: 16 warps / SM keep enough loads in flight
 layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dx,
@@ -74,13 +74,11 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
                      int rows, int D) {
   __shared__ float red[LN_WARPS][NV * 128 + 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 pg[NV], pb[NV], g4[NV];
+  float4 pg[NV], pb[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     pb[i] = pg[i];
-    const int c = (i * 32 + lane) * 4;
-    g4[i] = (c < D) ? *reinterpret_cast<const float4*>(gamma + c) : pg[i];
   }
   for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
     const float mu = mean[row], rs = rstd[row];
@@ -95,7 +93,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         pg[i].x += dyv[i].x * xh[i].x; pg[i].y += dyv[i].y * xh[i].y; pg[i].z += dyv[i].z * xh[i].z; pg[i].w += dyv[i].w * xh[i].w;
         pb[i].x += dyv[i].x; pb[i].y += dyv[i].y; pb[i].z += dyv[i].z; pb[i].w += dyv[i].w;
-        dyv[i].x *= g4[i].x; dyv[i].y *= g4[i].y; dyv[i].z *= g4[i].z; dyv[i].w *= g4[i].w;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));   // L1-resident, not worth 24 registers
+        dyv[i].x *= g4.x; dyv[i].y *= g4.y; dyv[i].z *= g4.z; dyv[i].w *= g4.w;
         s1 += dyv[i].x + dyv[i].y + dyv[i].z + dyv[i].w;
         s2 += dyv[i].x * xh[i].x + dyv[i].y * xh[i].y + dyv[i].z * xh[i].z + dyv[i].w * xh[i].w;
       }
@@ -150,28 +149,46 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, bf16* __r
   }
 }
 
-// out[n] += sum_m dy[m,n]; block = 32 x 8 threads, each block reduces a [rows_per_block, 32*VEC] slab.
+// out[n] += sum_m dy[m,n].  Block = 32 (16-byte column vectors) x 8 (rows); every warp load is 512 contiguous bytes,
+// 4 independent row loads in flight per thread; smem reduce over the 8 row-lanes, one atomicAdd per column per block.
 template <bool FP32>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ dy, long long ld, float* __restrict__ out, int M, int N, int rows_per_block) {
-  __shared__ float red[8][33];
+  constexpr int VEC = FP32 ? 4 : 8;
+  __shared__ float red[8][32 * VEC + 1];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int col = blockIdx.x * 32 + tx;
+  const int col = (blockIdx.x * 32 + tx) * VEC;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-  float s = 0.f;
-  if (col < N) {
-    for (int r = r0 + ty; r < r1; r += 8) {
-      if (FP32) s += reinterpret_cast<const float*>(dy)[(long long)r * ld + col];
-      else s += __bfloat162float(reinterpret_cast<const bf16*>(dy)[(long long)r * ld + col]);
-    }
-  }
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && col < N) {
-    float t = 0.f;
+  float acc[VEC];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w][tx];
-    atomicAdd(out + col, t);
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  if (col < N) {
+    auto add_row = [&](int r) {
+      if (FP32) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + (long long)r * ld + col));
+        acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+      } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(dy) + (long long)r * ld + col));
+        const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4 % VEC] += c.x; acc[5 % VEC] += c.y; acc[6 % VEC] += d.x; acc[7 % VEC] += d.y;
+      }
+    };
+    int r = r0 + ty;
+    for (; r + 24 < r1; r += 32) { add_row(r); add_row(r + 8); add_row(r + 16); add_row(r + 24); }
+    for (; r < r1; r += 8) add_row(r);
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) red[ty][tx * VEC + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int gc = blockIdx.x * 32 * VEC + c;
+    if (gc < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][c];
+      atomicAdd(out + gc, t);
+    }
   }
 }
 
@@ -190,7 +207,7 @@ template <int NV>
 int launch_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
                   const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, long long lddx,
                   void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 4);
+  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 8);
   layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx,
                                                           reinterpret_cast<bf16*>(dx16), dgamma, dbeta, rows, D);
   EGOVLP_CHECK_LAUNCH();
@@ -248,7 +265,10 @@ extern "C" int egovlp_colsum_accum(const void* dy, int dy_is_fp32, long long ld,
                                    void* stream) {
   EGOVLP_CHECK_ARG(dy && out && M >= 0 && N > 0, "colsum: bad args");
   if (M == 0) return EGOVLP_OK;
-  const int col_blocks = (N + 31) / 32;
+  const int vec = dy_is_fp32 ? 4 : 8;
+  EGOVLP_CHECK_ARG(N % vec == 0 && ld % vec == 0 && (reinterpret_cast<uintptr_t>(dy) & 15) == 0,
+                   "colsum: N=%d / ld=%lld must be multiples of %d and the base 16B aligned", N, ld, vec);
+  const int col_blocks = (N / vec + 31) / 32;
   int row_blocks = max(1, min((M + 63) / 64, (num_sms() * 8 + col_blocks - 1) / col_blocks));
   const int rows_per_block = (M + row_blocks - 1) / row_blocks;
   row_blocks = (M + rows_per_block - 1) / rows_per_block;
