@@ -14,6 +14,8 @@
 // Math: bf16 mma.sync m16n8k16 with fp32 accumulation + fp32 online softmax (exp2).  This op is HBM-bound on
 // B200 (<= 98 FLOP/B), so the legacy tensor path is sufficient to sit on the HBM roofline;
 // the tcgen05 pipeline is reserved for the GEMMs that carry 96% of the FLOPs.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "egovlp_b200.h"
 
@@ -593,12 +595,429 @@ __global__ void cls_grad_finalize_kernel(const float* __restrict__ dcls, bf16* _
   dqkv[(long long)b * S * 3 * D + which * D + h * HD + d] = __float2bfloat16(v);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Specialised ("fast") kernels.  Same math and layout as the generic kernels above, but the attendable region of
+// every 16-row tile is described by at most two key SPANS (multiples of 16 rows) instead of a per-element
+// group-id lookup, addresses of every ldmatrix are one add from per-thread constants, and masks are arithmetic and
+// only evaluated in the spans that need them:
+//   space : keys [0, NP&~15) unmasked, then the tail pair(s) holding the last patches, the CLS key and padding;
+//   time  (T in {4, 8, 16}, 112 patch rows per group, row = patch*T + frame):
+//           patch tiles see their own 16 keys (block-diagonal inside when T < 16) + the CLS pair,
+//           the CLS-query tile sees everything.
+// ------------------------------------------------------------------------------------------------------------
+struct FragOff {
+  uint32_t a[4];   // A fragments (and transposed B fragments): + tile + row0 * 128
+  uint32_t b[4];   // B fragments, n = rows: + tile + n0 * 128
+};
+__device__ __forceinline__ FragOff make_frag_off(int lane) {
+  FragOff f;
+  const int ra = (lane & 7) + ((lane >> 3) & 1) * 8, ca = lane >> 4;
+  const int rb = (lane & 7) + (lane >> 4) * 8, cb = (lane >> 3) & 1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f.a[k] = ra * ROW_BYTES + (((k * 2 + ca) ^ (ra & 7)) << 4);
+    f.b[k] = rb * ROW_BYTES + (((k * 2 + cb) ^ (rb & 7)) << 4);
+  }
+  return f;
+}
+
+struct Spans {
+  int lo[2], hi[2];
+  bool mask[2];
+};
+// other-side rows a 16-row tile starting at r0 interacts with
+template <bool TIME>
+__device__ __forceinline__ Spans tile_spans(const Geom& G, int r0, int valid_keys) {
+  Spans s;
+  const int NP = G.NP;
+  if (!TIME) {
+    s.lo[0] = 0; s.hi[0] = NP & ~15; s.mask[0] = false;
+    s.lo[1] = NP & ~15; s.hi[1] = G.NPAD; s.mask[1] = true;
+  } else if (r0 < NP) {
+    s.lo[0] = r0; s.hi[0] = r0 + 16; s.mask[0] = G.T < 16;
+    s.lo[1] = NP; s.hi[1] = NP + 16; s.mask[1] = true;
+  } else {
+    s.lo[0] = 0; s.hi[0] = NP; s.mask[0] = valid_keys < NP;
+    s.lo[1] = NP; s.hi[1] = NP + 16; s.mask[1] = true;
+  }
+  return s;
+}
+// may query row q attend key row k?
+template <bool TIME>
+__device__ __forceinline__ bool fast_valid(int q, int k, int NP, int sh, int valid_keys, bool first_group) {
+  if (k < NP) {
+    if (!TIME) return true;
+    return q == NP ? k < valid_keys : (q >> sh) == (k >> sh);
+  }
+  return k == NP && (q != NP || first_group);
+}
+
+template <bool TIME, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __restrict__ qkv, bf16* __restrict__ out,
+                     float* __restrict__ lse_out, float* __restrict__ cls_part, Geom G, int sh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  int b, h, g;
+  decode_block(G, b, h, g);
+  Smem sm;
+  load_group<false>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const bool first_group = (g == 0);
+  const int NP = G.NP;
+  const int valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : NP;
+  const FragOff fo = make_frag_off(lane);
+  const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
+  uint8_t* stage_gen = smem_gen + (stage - smem_base);
+
+  for (int rt = warp; rt * 16 <= NP; rt += NWARPS) {
+    const int r0 = rt * 16, rowA = r0 + gq, rowB = rowA + 8;
+    const Spans sp = tile_spans<TIME>(G, r0, valid_keys);
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) ldsm_x4(sm.q + r0 * ROW_BYTES + fo.a[kk], qf[kk]);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+
+#pragma unroll 1
+    for (int si = 0; si < 2; ++si) {
+#pragma unroll 1
+      for (int k0 = sp.lo[si]; k0 < sp.hi[si]; k0 += 64) {
+        const int npairs = min(4, (sp.hi[si] - k0) >> 4);
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (p < npairs) {
+            const uint32_t kb = sm.k + (k0 + 16 * p) * ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t bf[4];
+              ldsm_x4(kb + fo.b[kk], bf);
+              mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
+              mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
+            }
+          }
+        }
+        if (sp.mask[si]) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = k0 + 8 * j + 2 * t;
+            s[j][0] = fast_valid<TIME>(rowA, col, NP, sh, valid_keys, first_group) ? s[j][0] : -INFINITY;
+            s[j][1] = fast_valid<TIME>(rowA, col + 1, NP, sh, valid_keys, first_group) ? s[j][1] : -INFINITY;
+            s[j][2] = fast_valid<TIME>(rowB, col, NP, sh, valid_keys, first_group) ? s[j][2] : -INFINITY;
+            s[j][3] = fast_valid<TIME>(rowB, col + 1, NP, sh, valid_keys, first_group) ? s[j][3] : -INFINITY;
+          }
+        }
+        if (npairs < 4) {
+#pragma unroll
+          for (int j = 2; j < 8; ++j)
+            if (j >= 2 * npairs) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY; }
+        }
+        float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+          cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+        }
+        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+        const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+        const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0 * LOG2E, ms1 = (mn1 == -INFINITY) ? 0.f : mn1 * LOG2E;
+        const float a0 = exp2f(m0 * LOG2E - ms0), a1 = exp2f(m1 * LOG2E - ms1);
+        m0 = mn0; m1 = mn1;
+        l0 *= a0; l1 *= a1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p0 = exp2f(s[j][0] * LOG2E - ms0), p1 = exp2f(s[j][1] * LOG2E - ms0);
+          const float p2 = exp2f(s[j][2] * LOG2E - ms1), p3 = exp2f(s[j][3] * LOG2E - ms1);
+          l0 += p0 + p1; l1 += p2 + p3;
+          pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+          pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          if (kk < npairs) {
+            const uint32_t vb = sm.v + (k0 + 16 * kk) * ROW_BYTES;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+              uint32_t bf[4];
+              ldsm_x4_t(vb + fo.a[dp], bf);
+              mma_bf16(o[2 * dp], pf[kk], bf[0], bf[1]);
+              mma_bf16(o[2 * dp + 1], pf[kk], bf[2], bf[3]);
+            }
+          }
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    {
+      const int rc = NP - r0;   // local index of the CLS row in this tile, if any
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dst = cls_part + (((long long)(b * G.H + h)) * G.G + g) * 66;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dst[j * 8 + 2 * t] = hi_half ? o[j][2] : o[j][0];
+          dst[j * 8 + 2 * t + 1] = hi_half ? o[j][3] : o[j][1];
+        }
+        if (t == 0) { dst[64] = hi_half ? m1 : m0; dst[65] = hi_half ? l1 : l0; }
+      }
+    }
+    const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    if (t == 0) {
+      const int tok0 = row_token(G, g, rowA), tok1 = row_token(G, g, rowB);
+      if (tok0 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok0] = m0 + logf(l0);
+      if (tok1 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok1] = m1 + logf(l1);
+    }
+    store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
+  }
+}
+
+template <bool TIME, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB)
+fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const bf16* __restrict__ qkv, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                     const float* __restrict__ lse_in, bf16* __restrict__ dqkv, float* __restrict__ dcls, float q_scale,
+                     Geom G, int sh) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  int b, h, g;
+  decode_block(G, b, h, g);
+  Smem sm;
+  load_group<true>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const bool first_group = (g == 0);
+  const int NP = G.NP;
+  const int valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : NP;
+  const FragOff fo = make_frag_off(lane);
+
+  // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row
+  for (int r = warp * 4 + (lane >> 3); r < G.NPAD; r += NWARPS * 4) {
+    const int tok = row_token(G, g, r), c = lane & 7;
+    float d = 0.f;
+    if (tok >= 0) {
+      const uint4 ov = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + c * 8);
+      const uint4 dv = *reinterpret_cast<const uint4*>(smem_gen + (sw_addr(sm.dout, r, c) - smem_base));
+      const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 a = unpack_bf16x2(ou[i]), bb = unpack_bf16x2(du[i]);
+        d += a.x * bb.x + a.y * bb.y;
+      }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (c == 0) {
+      sm.delta[r] = d;
+      sm.lse[r] = tok >= 0 ? lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E : 0.f;
+    }
+  }
+  __syncthreads();
+
+  // phase 1: per 16 query rows -> dQ
+  for (int rt = warp; rt * 16 <= NP; rt += NWARPS) {
+    const int r0 = rt * 16, rowA = r0 + gq, rowB = rowA + 8;
+    const Spans sp = tile_spans<TIME>(G, r0, valid_keys);
+    const float ls0 = sm.lse[rowA], ls1 = sm.lse[rowB], de0 = sm.delta[rowA], de1 = sm.delta[rowB];
+    float dq[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
+#pragma unroll 1
+    for (int si = 0; si < 2; ++si) {
+#pragma unroll 1
+      for (int k0 = sp.lo[si]; k0 < sp.hi[si]; k0 += 32) {
+        const int npairs = min(2, (sp.hi[si] - k0) >> 4);
+        float s[4][4], dp[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (p < npairs) {
+            const uint32_t kb = sm.k + (k0 + 16 * p) * ROW_BYTES, vb = sm.v + (k0 + 16 * p) * ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t af[4], bf[4];
+              ldsm_x4(sm.q + r0 * ROW_BYTES + fo.a[kk], af);
+              ldsm_x4(kb + fo.b[kk], bf);
+              mma_bf16(s[2 * p], af, bf[0], bf[1]);
+              mma_bf16(s[2 * p + 1], af, bf[2], bf[3]);
+              ldsm_x4(sm.dout + r0 * ROW_BYTES + fo.a[kk], af);
+              ldsm_x4(vb + fo.b[kk], bf);
+              mma_bf16(dp[2 * p], af, bf[0], bf[1]);
+              mma_bf16(dp[2 * p + 1], af, bf[2], bf[3]);
+            }
+          }
+        }
+        uint32_t dsf[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = k0 + 8 * j + 2 * t;
+          bool v0 = j < 2 * npairs, v1 = v0, v2 = v0, v3 = v0;
+          if (sp.mask[si]) {
+            v0 = v0 && fast_valid<TIME>(rowA, col, NP, sh, valid_keys, first_group);
+            v1 = v1 && fast_valid<TIME>(rowA, col + 1, NP, sh, valid_keys, first_group);
+            v2 = v2 && fast_valid<TIME>(rowB, col, NP, sh, valid_keys, first_group);
+            v3 = v3 && fast_valid<TIME>(rowB, col + 1, NP, sh, valid_keys, first_group);
+          }
+          const float p0 = v0 ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
+          const float p1 = v1 ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
+          const float p2 = v2 ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
+          const float p3 = v3 ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
+          dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
+          dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (kk < npairs) {
+            const uint32_t kb = sm.k + (k0 + 16 * kk) * ROW_BYTES;
+#pragma unroll
+            for (int dpi = 0; dpi < 4; ++dpi) {
+              uint32_t bf[4];
+              ldsm_x4_t(kb + fo.a[dpi], bf);
+              mma_bf16(dq[2 * dpi], dsf[kk], bf[0], bf[1]);
+              mma_bf16(dq[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
+            }
+          }
+        }
+      }
+    }
+    {
+      const int rc = NP - r0;
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dst = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(dst + j * 8 + 2 * t, hi_half ? dq[j][2] : dq[j][0]);
+          atomicAdd(dst + j * 8 + 2 * t + 1, hi_half ? dq[j][3] : dq[j][1]);
+        }
+      }
+    }
+    store_frag_rows_bf16(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane);
+  }
+
+  // phase 2: per 16 keys -> dK, dV   (tile rows = keys, columns = queries)
+  for (int kt = warp; kt * 16 <= NP; kt += NWARPS) {
+    const int k0r = kt * 16, keyA = k0r + gq, keyB = keyA + 8;
+    const Spans sp = tile_spans<TIME>(G, k0r, valid_keys);
+    float dk[8][4], dv[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
+#pragma unroll 1
+    for (int si = 0; si < 2; ++si) {
+#pragma unroll 1
+      for (int q0 = sp.lo[si]; q0 < sp.hi[si]; q0 += 32) {
+        const int npairs = min(2, (sp.hi[si] - q0) >> 4);
+        float st[4][4], dpt[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f; }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          if (p < npairs) {
+            const uint32_t qb = sm.q + (q0 + 16 * p) * ROW_BYTES, db = sm.dout + (q0 + 16 * p) * ROW_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              uint32_t af[4], bf[4];
+              ldsm_x4(sm.k + k0r * ROW_BYTES + fo.a[kk], af);
+              ldsm_x4(qb + fo.b[kk], bf);
+              mma_bf16(st[2 * p], af, bf[0], bf[1]);
+              mma_bf16(st[2 * p + 1], af, bf[2], bf[3]);
+              ldsm_x4(sm.v + k0r * ROW_BYTES + fo.a[kk], af);
+              ldsm_x4(db + fo.b[kk], bf);
+              mma_bf16(dpt[2 * p], af, bf[0], bf[1]);
+              mma_bf16(dpt[2 * p + 1], af, bf[2], bf[3]);
+            }
+          }
+        }
+        uint32_t pf[2][4], dsf[2][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int col = q0 + 8 * j + 2 * t;       // query index
+          bool v0 = j < 2 * npairs, v1 = v0, v2 = v0, v3 = v0;
+          if (sp.mask[si]) {
+            v0 = v0 && fast_valid<TIME>(col, keyA, NP, sh, valid_keys, first_group);
+            v1 = v1 && fast_valid<TIME>(col + 1, keyA, NP, sh, valid_keys, first_group);
+            v2 = v2 && fast_valid<TIME>(col, keyB, NP, sh, valid_keys, first_group);
+            v3 = v3 && fast_valid<TIME>(col + 1, keyB, NP, sh, valid_keys, first_group);
+          }
+          const float2 lq = *reinterpret_cast<const float2*>(sm.lse + col);
+          const float2 dq2 = *reinterpret_cast<const float2*>(sm.delta + col);
+          const float p0 = v0 ? exp2f(st[j][0] * LOG2E - lq.x) : 0.f;
+          const float p1 = v1 ? exp2f(st[j][1] * LOG2E - lq.y) : 0.f;
+          const float p2 = v2 ? exp2f(st[j][2] * LOG2E - lq.x) : 0.f;
+          const float p3 = v3 ? exp2f(st[j][3] * LOG2E - lq.y) : 0.f;
+          pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+          pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+          dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq2.x), p1 * (dpt[j][1] - dq2.y));
+          dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dpt[j][2] - dq2.x), p3 * (dpt[j][3] - dq2.y));
+        }
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          if (kk < npairs) {
+            const uint32_t qb = sm.q + (q0 + 16 * kk) * ROW_BYTES, db = sm.dout + (q0 + 16 * kk) * ROW_BYTES;
+#pragma unroll
+            for (int dpi = 0; dpi < 4; ++dpi) {
+              uint32_t bf[4];
+              ldsm_x4_t(db + fo.a[dpi], bf);
+              mma_bf16(dv[2 * dpi], pf[kk], bf[0], bf[1]);
+              mma_bf16(dv[2 * dpi + 1], pf[kk], bf[2], bf[3]);
+              ldsm_x4_t(qb + fo.a[dpi], bf);
+              mma_bf16(dk[2 * dpi], dsf[kk], bf[0], bf[1]);
+              mma_bf16(dk[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
+            }
+          }
+        }
+      }
+    }
+    {
+      const int rc = NP - k0r;
+      if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
+        const bool hi_half = rc >= 8;
+        float* dstk = dcls + ((long long)(b * G.H + h) * 3 + 1) * HD;
+        float* dstv = dcls + ((long long)(b * G.H + h) * 3 + 2) * HD;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(dstk + j * 8 + 2 * t, hi_half ? dk[j][2] : dk[j][0]);
+          atomicAdd(dstk + j * 8 + 2 * t + 1, hi_half ? dk[j][3] : dk[j][1]);
+          atomicAdd(dstv + j * 8 + 2 * t, hi_half ? dv[j][2] : dv[j][0]);
+          atomicAdd(dstv + j * 8 + 2 * t + 1, hi_half ? dv[j][3] : dv[j][1]);
+        }
+      }
+    }
+    store_frag_rows_bf16(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane);
+    store_frag_rows_bf16(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane);
+  }
+}
+
+// EGOVLP_ATTN_GENERIC=1 routes every geometry through the generic group-id kernels (used by the tests to check
+// both implementations against the oracle)
+inline bool force_generic() {
+  const char* e = getenv("EGOVLP_ATTN_GENERIC");
+  return e && e[0] == '1';
+}
+// time-mode fast path: T in {4, 8, 16} with full 112-row groups
+inline bool time_fast_ok(const Geom& G) { return G.mode == 0 && (G.T == 4 || G.T == 8 || G.T == 16) && G.NP == 112; }
+inline int time_shift(const Geom& G) { return G.T == 16 ? 4 : G.T == 8 ? 3 : 2; }
+
 int make_geom(Geom& G, int B, int T, int N, int H, int mode) {
   G.B = B; G.H = H; G.T = T; G.N = N; G.S = 1 + T * N; G.D = H * HD; G.mode = mode;
   if (mode == 1) {
     G.PG = N; G.G = T; G.NP = N; G.gsize = N;
   } else {
-    G.PG = min(N, 127 / T);
+    G.PG = (T <= 16 && 16 % T == 0) ? min(N, 112 / T) : min(N, 127 / T);   // 112-row groups keep the CLS row tile-aligned
     if (G.PG < 1) return EGOVLP_ERR_UNSUPPORTED;
     G.G = (N + G.PG - 1) / G.PG; G.NP = G.PG * T; G.gsize = T;
   }
@@ -643,21 +1062,26 @@ extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, f
   int rc = make_group_tmap(&tm, qkv, G, 3 * H);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (G.NPAD > 128) {   // space, 196 patches: 13 row tiles over 7 warps, 2 CTAs / SM
-    constexpr int W = 7;
-    const size_t smem = attn_smem_bytes(G, false, W);
-    auto kern = divided_attn_fwd_kernel<W, 2>;
-    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * H * G.G, W * 32, smem, st>>>(tm, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse,
-                                           cls_part, G);
-  } else {              // time (<= 8 row tiles) and small test geometries
-    constexpr int W = 4;
-    const size_t smem = attn_smem_bytes(G, false, W);
-    auto kern = divided_attn_fwd_kernel<W, 3>;
-    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * H * G.G, W * 32, smem, st>>>(tm, reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(out), lse,
-                                           cls_part, G);
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  bf16* o = reinterpret_cast<bf16*>(out);
+  const int grid = B * H * G.G;
+#define LAUNCH_FWD(KERN, W, ...)                                                                              \
+  do {                                                                                                        \
+    const size_t smem = attn_smem_bytes(G, false, W);                                                         \
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    KERN<<<grid, W * 32, smem, st>>>(tm, q, o, lse, cls_part, G, ##__VA_ARGS__);                              \
+  } while (0)
+  const bool generic = force_generic() || (mode == 0 && !time_fast_ok(G));
+  if (generic) {
+    if (G.NPAD > 128) LAUNCH_FWD((divided_attn_fwd_kernel<7, 2>), 7);
+    else LAUNCH_FWD((divided_attn_fwd_kernel<4, 3>), 4);
+  } else if (mode == 1) {     // space: 13 row tiles over 7 warps, 2 CTAs / SM at 196 patches
+    if (G.NPAD > 128) LAUNCH_FWD((fast_attn_fwd_kernel<false, 7, 2>), 7, 0);
+    else LAUNCH_FWD((fast_attn_fwd_kernel<false, 4, 3>), 4, 0);
+  } else {                    // time: 8 row tiles over 4 warps, 3 CTAs / SM
+    LAUNCH_FWD((fast_attn_fwd_kernel<true, 4, 3>), 4, time_shift(G));
   }
+#undef LAUNCH_FWD
   EGOVLP_CHECK_LAUNCH();
   const int BH = B * H;
   cls_merge_kernel<<<(BH + 3) / 4, 128, 0, st>>>(cls_part, reinterpret_cast<bf16*>(out), lse, BH, H, G.G, G.S, G.D);
@@ -679,23 +1103,28 @@ extern "C" int egovlp_divided_attn_bwd(const void* qkv, const void* out, const v
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   EGOVLP_CHECK_CUDA(cudaMemsetAsync(dcls_ws, 0, (size_t)B * H * 3 * HD * sizeof(float), st));
-  if (G.NPAD > 128) {   // space: 13 row tiles over 7 warps, 1 CTA / SM (4 tiles of 26 KB), up to 255 registers
-    constexpr int W = 7;     // 2 CTAs / SM: 4 x 26 KB tiles each, no staging
-    const size_t smem = attn_smem_bytes(G, true, W);
-    auto kern = divided_attn_bwd_kernel<W, 2>;
-    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * H * G.G, W * 32, smem, st>>>(tmq, tmd, reinterpret_cast<const bf16*>(qkv),
-                                           reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), lse,
-                                           reinterpret_cast<bf16*>(dqkv), dcls_ws, q_scale, G);
+  const bf16* q = reinterpret_cast<const bf16*>(qkv);
+  const bf16* o = reinterpret_cast<const bf16*>(out);
+  const bf16* d_o = reinterpret_cast<const bf16*>(dout);
+  bf16* dq = reinterpret_cast<bf16*>(dqkv);
+  const int grid = B * H * G.G;
+#define LAUNCH_BWD(KERN, W, ...)                                                                              \
+  do {                                                                                                        \
+    const size_t smem = attn_smem_bytes(G, true, W);                                                          \
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    KERN<<<grid, W * 32, smem, st>>>(tmq, tmd, q, o, d_o, lse, dq, dcls_ws, q_scale, G, ##__VA_ARGS__);       \
+  } while (0)
+  const bool generic = force_generic() || (mode == 0 && !time_fast_ok(G));
+  if (generic) {
+    if (G.NPAD > 128) LAUNCH_BWD((divided_attn_bwd_kernel<7, 2>), 7);
+    else LAUNCH_BWD((divided_attn_bwd_kernel<4, 3>), 4);
+  } else if (mode == 1) {     // space: 2 CTAs / SM (4 x 26 KB tiles each, no staging)
+    if (G.NPAD > 128) LAUNCH_BWD((fast_attn_bwd_kernel<false, 7, 2>), 7, 0);
+    else LAUNCH_BWD((fast_attn_bwd_kernel<false, 4, 3>), 4, 0);
   } else {
-    constexpr int W = 4;
-    const size_t smem = attn_smem_bytes(G, true, W);
-    auto kern = divided_attn_bwd_kernel<W, 3>;
-    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<B * H * G.G, W * 32, smem, st>>>(tmq, tmd, reinterpret_cast<const bf16*>(qkv),
-                                           reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), lse,
-                                           reinterpret_cast<bf16*>(dqkv), dcls_ws, q_scale, G);
+    LAUNCH_BWD((fast_attn_bwd_kernel<true, 4, 3>), 4, time_shift(G));
   }
+#undef LAUNCH_BWD
   EGOVLP_CHECK_LAUNCH();
   const int n = B * H * 3 * HD;
   cls_grad_finalize_kernel<<<(n + 255) / 256, 256, 0, st>>>(dcls_ws, reinterpret_cast<bf16*>(dqkv), B, H, G.S, G.D, q_scale);
