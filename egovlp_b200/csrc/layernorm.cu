@@ -65,9 +65,9 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
   }
 }
 
-template <int NV>
+template <int NV, bool DY16>
 __global__ void __launch_bounds__(LN_WARPS * 32, 2)   // <=128 registers: 16 warps / SM keep enough loads in flight
-layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ x, long long ldx,
+layernorm_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dx,
                      long long lddx, bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -88,7 +88,13 @@ layernorm_bwd_kernel(const float* __restrict__ dy, long long lddy, const float* 
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
-        dyv[i] = *reinterpret_cast<const float4*>(dy + (long long)row * lddy + c);
+        if (DY16) {
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (long long)row * lddy + c);
+          const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+          dyv[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          dyv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (long long)row * lddy + c);
+        }
         const float4 xv = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
         pg[i].x += dyv[i].x * xh[i].x; pg[i].y += dyv[i].y * xh[i].y; pg[i].z += dyv[i].z * xh[i].z; pg[i].w += dyv[i].w * xh[i].w;
@@ -204,12 +210,18 @@ int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_ou
 }
 
 template <int NV>
-int launch_ln_bwd(const float* dy, long long lddy, const float* x, long long ldx, const float* gamma,
+int launch_ln_bwd(const void* dy, int dy16, long long lddy, const float* x, long long ldx, const float* gamma,
                   const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, long long lddx,
                   void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
   const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 8);
-  layernorm_bwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx,
-                                                          reinterpret_cast<bf16*>(dx16), dgamma, dbeta, rows, D);
+  if (dy16)
+    layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
+                                                                  lddx, reinterpret_cast<bf16*>(dx16), dgamma, dbeta,
+                                                                  rows, D);
+  else
+    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
+                                                                   lddx, reinterpret_cast<bf16*>(dx16), dgamma, dbeta,
+                                                                   rows, D);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
@@ -233,7 +245,7 @@ extern "C" int egovlp_layernorm_fwd(const float* x, long long ldx, const float* 
   return EGOVLP_ERR_UNSUPPORTED;
 }
 
-extern "C" int egovlp_layernorm_bwd(const float* dy, long long lddy, const float* x, long long ldx,
+extern "C" int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx,
                                     const float* gamma, const float* mean, const float* rstd, const float* add1,
                                     const float* add2, float* dx, long long lddx, void* dx_bf16, float* dgamma,
                                     float* dbeta, int rows, int D, void* stream) {
@@ -242,7 +254,7 @@ extern "C" int egovlp_layernorm_bwd(const float* dy, long long lddy, const float
   if (rows == 0) return EGOVLP_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (D + 127) / 128;
-#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
+#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, dy_is_bf16, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
   switch (nv) { LN_BWD_CASE(1); LN_BWD_CASE(2); LN_BWD_CASE(3); LN_BWD_CASE(4); LN_BWD_CASE(5); LN_BWD_CASE(6); LN_BWD_CASE(7); LN_BWD_CASE(8); }
 #undef LN_BWD_CASE
   return EGOVLP_ERR_UNSUPPORTED;

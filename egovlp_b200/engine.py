@@ -192,7 +192,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         du = _empty((M, HID), BF16, dy)
         ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=2)               # (dy W2) * gelu'(u)
         g_f1w, g_f1b = wgrad(du, n2, HID, D), bgrad(du)
-        dn2 = _empty((M, D), F32, dy)
+        dn2 = _empty((M, D), BF16, dy)                       # LayerNorm-input gradients travel as bf16
         ops.gemm(du, cache.get(f1w), dn2, b_mn=True)
         del du
         dsr, dsr16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
@@ -206,7 +206,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
             ops.gemm(dres16, cache.get(pw), da, b_mn=True)
             dqkv = ops.divided_attn_bwd(qkv, a, da, lse, B, T, N, H, mode, Q_SCALE)
             g_qw, g_qb = wgrad(dqkv, inp16, 3 * D, D), bgrad(dqkv)
-            dinp = _empty((M, D), F32, dres)
+            dinp = _empty((M, D), BF16, dres)
             ops.gemm(dqkv, cache.get(qw), dinp, b_mn=True)
             return g_qw, g_qb, g_pw, g_pb, dinp
 

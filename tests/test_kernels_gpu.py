@@ -111,6 +111,7 @@ def test_layernorm_fwd_bwd(ops, rows, D):
     ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
     assert rel_err(y32, ref) < 1e-5 and rel_err(y16, ref) < 4e-3
     dy = mk((rows, D), 23, dtype=torch.float32)
+    dy16 = dy.to(torch.bfloat16)
     a1, a2 = mk((rows, D), 24, dtype=torch.float32), mk((rows, D), 25, dtype=torch.float32)
     ref.backward(dy)
     dx = torch.empty_like(x)
@@ -120,6 +121,11 @@ def test_layernorm_fwd_bwd(ops, rows, D):
     assert rel_err(dx, xr.grad + a1 + a2) < 1e-5
     assert rel_err(dx16, xr.grad + a1 + a2) < 4e-3
     assert rel_err(dg, gr.grad) < 1e-4 and rel_err(db, br.grad) < 1e-4
+    # bf16 upstream gradient (what the dgrad GEMMs hand over)
+    ref2 = torch.nn.functional.layer_norm(xr2 := x.clone().requires_grad_(True), (D,), g, b, 1e-6)
+    ref2.backward(dy16.float())
+    ops.layernorm_bwd(dy16, x, g, mean, rstd, dx=dx)
+    assert rel_err(dx, xr2.grad) < 1e-5
 
 
 def test_layernorm_fused_add(ops):
