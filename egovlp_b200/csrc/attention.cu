@@ -652,6 +652,33 @@ __device__ __forceinline__ bool fast_valid(int q, int k, int NP, int sh, int val
   return k == NP && (q != NP || first_group);
 }
 
+// Work items of a CTA.  space: the 16-row tiles 0 .. NP/16 (the last one holds the CLS row).  time: the NP/16 patch
+// tiles, then the CLS row split into NWARPS key (or query) parts of NPAD/NWARPS rows each -- the CLS row would
+// otherwise be one warp's serial tail; its results are partials / atomics anyway, so the parts need no reduction.
+template <bool TIME, int NWARPS>
+__device__ __forceinline__ bool work_item(const Geom& G, int it, int valid_keys, int& r0, int& part, Spans& sp) {
+  part = 0;
+  if (!TIME) {
+    r0 = it * 16;
+    if (r0 > G.NP) return false;
+    sp = tile_spans<false>(G, r0, valid_keys);
+    return true;
+  }
+  const int n_tiles = G.NP >> 4;
+  if (it < n_tiles) {
+    r0 = it * 16;
+    sp = tile_spans<true>(G, r0, valid_keys);
+    return true;
+  }
+  part = it - n_tiles;
+  if (part >= NWARPS) return false;
+  const int w = G.NPAD / NWARPS;
+  r0 = G.NP;
+  sp.lo[0] = part * w; sp.hi[0] = part * w + w; sp.mask[0] = true;
+  sp.lo[1] = 0; sp.hi[1] = 0; sp.mask[1] = false;
+  return true;
+}
+
 template <bool TIME, int NWARPS, int MINB>
 __global__ void __launch_bounds__(NWARPS * 32, MINB)
 fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __restrict__ qkv, bf16* __restrict__ out,
@@ -673,9 +700,11 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
   const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
   uint8_t* stage_gen = smem_gen + (stage - smem_base);
 
-  for (int rt = warp; rt * 16 <= NP; rt += NWARPS) {
-    const int r0 = rt * 16, rowA = r0 + gq, rowB = rowA + 8;
-    const Spans sp = tile_spans<TIME>(G, r0, valid_keys);
+  for (int it = warp;; it += NWARPS) {
+    int r0, part;
+    Spans sp;
+    if (!work_item<TIME, NWARPS>(G, it, valid_keys, r0, part, sp)) break;
+    const int rowA = r0 + gq, rowB = rowA + 8;
     uint32_t qf[4][4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) ldsm_x4(sm.q + r0 * ROW_BYTES + fo.a[kk], qf[kk]);
@@ -765,7 +794,8 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
       const int rc = NP - r0;   // local index of the CLS row in this tile, if any
       if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
         const bool hi_half = rc >= 8;
-        float* dst = cls_part + (((long long)(b * G.H + h)) * G.G + g) * 66;
+        constexpr int PARTS = TIME ? NWARPS : 1;
+        float* dst = cls_part + ((((long long)(b * G.H + h)) * G.G + g) * PARTS + part) * 66;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           dst[j * 8 + 2 * t] = hi_half ? o[j][2] : o[j][0];
@@ -774,6 +804,7 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
         if (t == 0) { dst[64] = hi_half ? m1 : m0; dst[65] = hi_half ? l1 : l0; }
       }
     }
+    if (TIME && r0 == NP) continue;     // a CLS part: nothing else to store
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     if (t == 0) {
       const int tok0 = row_token(G, g, rowA), tok1 = row_token(G, g, rowB);
@@ -828,9 +859,11 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   __syncthreads();
 
   // phase 1: per 16 query rows -> dQ
-  for (int rt = warp; rt * 16 <= NP; rt += NWARPS) {
-    const int r0 = rt * 16, rowA = r0 + gq, rowB = rowA + 8;
-    const Spans sp = tile_spans<TIME>(G, r0, valid_keys);
+  for (int it = warp;; it += NWARPS) {
+    int r0, part;
+    Spans sp;
+    if (!work_item<TIME, NWARPS>(G, it, valid_keys, r0, part, sp)) break;
+    const int rowA = r0 + gq, rowB = rowA + 8;
     const float ls0 = sm.lse[rowA], ls1 = sm.lse[rowB], de0 = sm.delta[rowA], de1 = sm.delta[rowB];
     float dq[8][4];
 #pragma unroll
@@ -910,9 +943,11 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   }
 
   // phase 2: per 16 keys -> dK, dV   (tile rows = keys, columns = queries)
-  for (int kt = warp; kt * 16 <= NP; kt += NWARPS) {
-    const int k0r = kt * 16, keyA = k0r + gq, keyB = keyA + 8;
-    const Spans sp = tile_spans<TIME>(G, k0r, valid_keys);
+  for (int it = warp;; it += NWARPS) {
+    int k0r, part;
+    Spans sp;
+    if (!work_item<TIME, NWARPS>(G, it, valid_keys, k0r, part, sp)) break;
+    const int keyA = k0r + gq, keyB = keyA + 8;
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
@@ -1049,7 +1084,7 @@ using namespace egovlp;
 extern "C" long long egovlp_divided_attn_workspace_floats(int B, int T, int N, int H, int mode) {
   Geom G;
   if (make_geom(G, B, T, N, H, mode)) return -1;
-  return (long long)B * H * G.G * 66;
+  return (long long)B * H * G.G * 4 * 66;    // up to 4 CLS-row partials per group
 }
 
 extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N,
@@ -1084,7 +1119,8 @@ extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, f
 #undef LAUNCH_FWD
   EGOVLP_CHECK_LAUNCH();
   const int BH = B * H;
-  cls_merge_kernel<<<(BH + 3) / 4, 128, 0, st>>>(cls_part, reinterpret_cast<bf16*>(out), lse, BH, H, G.G, G.S, G.D);
+  const int parts = (!generic && mode == 0) ? 4 : 1;      // fast time kernel: CLS row split over its 4 warps
+  cls_merge_kernel<<<(BH + 3) / 4, 128, 0, st>>>(cls_part, o, lse, BH, H, G.G * parts, G.S, G.D);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }

@@ -29,8 +29,8 @@ def test_argument_errors_are_reported_not_swallowed():
     with pytest.raises(_lib.EgovlpError, match="null pointer"):
         _lib.call("egovlp_layernorm_fwd", None, C.c_longlong(0), None, None, None, None, None, None, None, None, 4, 768,
                   C.c_float(1e-6), None)
-    assert _lib.lib().egovlp_divided_attn_workspace_floats(2, 16, 196, 12, 0) == 2 * 12 * 28 * 66
-    assert _lib.lib().egovlp_divided_attn_workspace_floats(2, 16, 196, 12, 1) == 2 * 12 * 16 * 66
+    assert _lib.lib().egovlp_divided_attn_workspace_floats(2, 16, 196, 12, 0) == 2 * 12 * 28 * 4 * 66
+    assert _lib.lib().egovlp_divided_attn_workspace_floats(2, 16, 196, 12, 1) == 2 * 12 * 16 * 4 * 66
     assert _lib.lib().egovlp_divided_attn_workspace_floats(2, 400, 196, 12, 0) == -1     # unsupported geometry
 
 
