@@ -596,14 +596,16 @@ __global__ void cls_grad_finalize_kernel(const float* __restrict__ dcls, bf16* _
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Specialised ("fast") kernels.  Same math and layout as the generic kernels above, but the attendable region of
-// every 16-row tile is described by at most two key SPANS (multiples of 16 rows) instead of a per-element
-// group-id lookup, addresses of every ldmatrix are one add from per-thread constants, and masks are arithmetic and
-// only evaluated in the spans that need them:
-//   space : keys [0, NP&~15) unmasked, then the tail pair(s) holding the last patches, the CLS key and padding;
-//   time  (T in {4, 8, 16}, 112 patch rows per group, row = patch*T + frame):
-//           patch tiles see their own 16 keys (block-diagonal inside when T < 16) + the CLS pair,
-//           the CLS-query tile sees everything.
+// Specialised ("fast") kernels.  Same math and layout as the generic kernels above, but the rows a 16-row tile
+// interacts with are given as CHUNKS of 1-4 sixteen-row "pairs" (pair = two 8-wide mma n-tiles) instead of a
+// per-element group-id lookup; the chunk body is compiled per pair count, ldmatrix addresses are one add from
+// per-thread constants, and masks are arithmetic and only evaluated for the pairs that need them:
+//   space : pairs 0,16,..  in chunks of 4 (fwd) / 2 (bwd); only the tail pair(s) (last patches, CLS key, padding)
+//           are masked;
+//   time  (T in {4, 8, 16}; 112 patch rows per group, row = patch*T + frame):
+//           a patch tile sees ONE chunk of two pairs: its own 16 rows (block-diagonal inside when T < 16) and the
+//           CLS pair; the CLS row is split into NWARPS parts of 32 rows, one chunk each (its results are
+//           partials / atomics anyway, so the parts need no reduction).
 // ------------------------------------------------------------------------------------------------------------
 struct FragOff {
   uint32_t a[4];   // A fragments (and transposed B fragments): + tile + row0 * 128
@@ -621,62 +623,137 @@ __device__ __forceinline__ FragOff make_frag_off(int lane) {
   return f;
 }
 
-struct Spans {
-  int lo[2], hi[2];
-  bool mask[2];
+struct Chunk {
+  int np;          // pairs in this chunk (1..4)
+  int base[4];     // first row of each pair on the other side
+  uint32_t mask;   // bit p: pair p needs masking
 };
-// other-side rows a 16-row tile starting at r0 interacts with
-template <bool TIME>
-__device__ __forceinline__ Spans tile_spans(const Geom& G, int r0, int valid_keys) {
-  Spans s;
-  const int NP = G.NP;
-  if (!TIME) {
-    s.lo[0] = 0; s.hi[0] = NP & ~15; s.mask[0] = false;
-    s.lo[1] = NP & ~15; s.hi[1] = G.NPAD; s.mask[1] = true;
-  } else if (r0 < NP) {
-    s.lo[0] = r0; s.hi[0] = r0 + 16; s.mask[0] = G.T < 16;
-    s.lo[1] = NP; s.hi[1] = NP + 16; s.mask[1] = true;
-  } else {
-    s.lo[0] = 0; s.hi[0] = NP; s.mask[0] = valid_keys < NP;
-    s.lo[1] = NP; s.hi[1] = NP + 16; s.mask[1] = true;
-  }
-  return s;
-}
+
+struct FastCtx {
+  int NP, NPAD, sh, valid_keys;
+  bool first_group;
+};
+
 // may query row q attend key row k?
 template <bool TIME>
-__device__ __forceinline__ bool fast_valid(int q, int k, int NP, int sh, int valid_keys, bool first_group) {
-  if (k < NP) {
+__device__ __forceinline__ bool fast_valid(const FastCtx& c, int q, int k) {
+  if (k < c.NP) {
     if (!TIME) return true;
-    return q == NP ? k < valid_keys : (q >> sh) == (k >> sh);
+    return q == c.NP ? k < c.valid_keys : (q >> c.sh) == (k >> c.sh);
   }
-  return k == NP && (q != NP || first_group);
+  return k == c.NP && (q != c.NP || c.first_group);
 }
 
-// Work items of a CTA.  space: the 16-row tiles 0 .. NP/16 (the last one holds the CLS row).  time: the NP/16 patch
-// tiles, then the CLS row split into NWARPS key (or query) parts of NPAD/NWARPS rows each -- the CLS row would
-// otherwise be one warp's serial tail; its results are partials / atomics anyway, so the parts need no reduction.
+// Work items of a CTA: (r0, part).  space: 16-row tiles 0 .. NP/16.  time: NP/16 patch tiles, then NWARPS CLS parts.
 template <bool TIME, int NWARPS>
-__device__ __forceinline__ bool work_item(const Geom& G, int it, int valid_keys, int& r0, int& part, Spans& sp) {
-  part = 0;
+__device__ __forceinline__ bool work_item(const FastCtx& c, int it, int& r0, int& part) {
+  part = -1;
   if (!TIME) {
     r0 = it * 16;
-    if (r0 > G.NP) return false;
-    sp = tile_spans<false>(G, r0, valid_keys);
-    return true;
+    return r0 <= c.NP;
   }
-  const int n_tiles = G.NP >> 4;
-  if (it < n_tiles) {
-    r0 = it * 16;
-    sp = tile_spans<true>(G, r0, valid_keys);
-    return true;
-  }
+  const int n_tiles = c.NP >> 4;
+  if (it < n_tiles) { r0 = it * 16; return true; }
   part = it - n_tiles;
-  if (part >= NWARPS) return false;
-  const int w = G.NPAD / NWARPS;
-  r0 = G.NP;
-  sp.lo[0] = part * w; sp.hi[0] = part * w + w; sp.mask[0] = true;
-  sp.lo[1] = 0; sp.hi[1] = 0; sp.mask[1] = false;
+  r0 = c.NP;
+  return part < NWARPS;
+}
+// chunk `ci` of a work item, CW = pairs per chunk in the dense (space) case; returns false when past the end
+template <bool TIME, int NWARPS, int CW>
+__device__ __forceinline__ bool get_chunk(const FastCtx& c, int T, int r0, int part, int ci, Chunk& ch) {
+  if (TIME) {
+    if (ci > 0 && (part < 0 || CW >= 2)) return false;
+    if (part < 0) {                 // patch tile: own rows + the CLS pair
+      ch.np = 2; ch.base[0] = r0; ch.base[1] = c.NP; ch.mask = (T < 16 ? 1u : 0u) | 2u;
+      return true;
+    }
+    const int w = c.NPAD / NWARPS;  // CLS part: w (= 32) consecutive rows
+    if (CW >= 2) { ch.np = 2; ch.base[0] = part * w; ch.base[1] = part * w + 16; ch.mask = 3u; return true; }
+    if (ci >= 2) return false;
+    ch.np = 1; ch.base[0] = part * w + 16 * ci; ch.mask = 1u;
+    return true;
+  }
+  const int k0 = ci * CW * 16;
+  if (k0 >= c.NPAD) return false;
+  ch.np = min(CW, (c.NPAD - k0) >> 4);
+  ch.mask = 0;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    ch.base[p] = k0 + 16 * p;
+    if (p < ch.np && k0 + 16 * p + 16 > (c.NP & ~15)) ch.mask |= 1u << p;
+  }
   return true;
+}
+
+// ---- forward chunk: S = Q K^T over NPR pairs, online softmax update, O += P V
+template <bool TIME, int NPR>
+__device__ __forceinline__ void fwd_chunk(const FastCtx& c, const Smem& sm, const FragOff& fo, const Chunk& ch,
+                                          const uint32_t (&qf)[4][4], int rowA, int rowB, int t, float& m0, float& m1,
+                                          float& l0, float& l1, float (&o)[8][4]) {
+  float s[2 * NPR][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NPR; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const uint32_t kb = sm.k + ch.base[p] * ROW_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t bf[4];
+      ldsm_x4(kb + fo.b[kk], bf);
+      mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
+      mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
+    }
+  }
+  if (ch.mask) {
+#pragma unroll
+    for (int p = 0; p < NPR; ++p) {
+      if (ch.mask & (1u << p)) {
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;
+          s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
+          s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
+          s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
+          s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
+        }
+      }
+    }
+  }
+  float cm0 = -INFINITY, cm1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 2 * NPR; ++j) {
+    cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
+    cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
+  }
+  cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
+  cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
+  const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
+  const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0 * LOG2E, ms1 = (mn1 == -INFINITY) ? 0.f : mn1 * LOG2E;
+  const float a0 = exp2f(m0 * LOG2E - ms0), a1 = exp2f(m1 * LOG2E - ms1);
+  m0 = mn0; m1 = mn1;
+  l0 *= a0; l1 *= a1;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+  uint32_t pf[NPR][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NPR; ++j) {
+    const float p0 = exp2f(s[j][0] * LOG2E - ms0), p1 = exp2f(s[j][1] * LOG2E - ms0);
+    const float p2 = exp2f(s[j][2] * LOG2E - ms1), p3 = exp2f(s[j][3] * LOG2E - ms1);
+    l0 += p0 + p1; l1 += p2 + p3;
+    pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
+    pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const uint32_t vb = sm.v + ch.base[p] * ROW_BYTES;
+#pragma unroll
+    for (int dp = 0; dp < 4; ++dp) {
+      uint32_t bf[4];
+      ldsm_x4_t(vb + fo.a[dp], bf);
+      mma_bf16(o[2 * dp], pf[p], bf[0], bf[1]);
+      mma_bf16(o[2 * dp + 1], pf[p], bf[2], bf[3]);
+    }
+  }
 }
 
 template <bool TIME, int NWARPS, int MINB>
@@ -693,17 +770,16 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const bool first_group = (g == 0);
-  const int NP = G.NP;
-  const int valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : NP;
+  FastCtx c;
+  c.NP = G.NP; c.NPAD = G.NPAD; c.sh = sh; c.first_group = (g == 0);
+  c.valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : G.NP;
   const FragOff fo = make_frag_off(lane);
   const uint32_t stage = sm.stage + warp * 16 * ROW_BYTES;
   uint8_t* stage_gen = smem_gen + (stage - smem_base);
 
   for (int it = warp;; it += NWARPS) {
     int r0, part;
-    Spans sp;
-    if (!work_item<TIME, NWARPS>(G, it, valid_keys, r0, part, sp)) break;
+    if (!work_item<TIME, NWARPS>(c, it, r0, part)) break;
     const int rowA = r0 + gq, rowB = rowA + 8;
     uint32_t qf[4][4];
 #pragma unroll
@@ -712,90 +788,24 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
     float o[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
-
+    Chunk ch;
 #pragma unroll 1
-    for (int si = 0; si < 2; ++si) {
-#pragma unroll 1
-      for (int k0 = sp.lo[si]; k0 < sp.hi[si]; k0 += 64) {
-        const int npairs = min(4, (sp.hi[si] - k0) >> 4);
-        float s[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          if (p < npairs) {
-            const uint32_t kb = sm.k + (k0 + 16 * p) * ROW_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              uint32_t bf[4];
-              ldsm_x4(kb + fo.b[kk], bf);
-              mma_bf16(s[2 * p], qf[kk], bf[0], bf[1]);
-              mma_bf16(s[2 * p + 1], qf[kk], bf[2], bf[3]);
-            }
-          }
-        }
-        if (sp.mask[si]) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = k0 + 8 * j + 2 * t;
-            s[j][0] = fast_valid<TIME>(rowA, col, NP, sh, valid_keys, first_group) ? s[j][0] : -INFINITY;
-            s[j][1] = fast_valid<TIME>(rowA, col + 1, NP, sh, valid_keys, first_group) ? s[j][1] : -INFINITY;
-            s[j][2] = fast_valid<TIME>(rowB, col, NP, sh, valid_keys, first_group) ? s[j][2] : -INFINITY;
-            s[j][3] = fast_valid<TIME>(rowB, col + 1, NP, sh, valid_keys, first_group) ? s[j][3] : -INFINITY;
-          }
-        }
-        if (npairs < 4) {
-#pragma unroll
-          for (int j = 2; j < 8; ++j)
-            if (j >= 2 * npairs) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = -INFINITY; }
-        }
-        float cm0 = -INFINITY, cm1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          cm0 = fmaxf(cm0, fmaxf(s[j][0], s[j][1]));
-          cm1 = fmaxf(cm1, fmaxf(s[j][2], s[j][3]));
-        }
-        cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 1)); cm0 = fmaxf(cm0, __shfl_xor_sync(0xffffffffu, cm0, 2));
-        cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 1)); cm1 = fmaxf(cm1, __shfl_xor_sync(0xffffffffu, cm1, 2));
-        const float mn0 = fmaxf(m0, cm0), mn1 = fmaxf(m1, cm1);
-        const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0 * LOG2E, ms1 = (mn1 == -INFINITY) ? 0.f : mn1 * LOG2E;
-        const float a0 = exp2f(m0 * LOG2E - ms0), a1 = exp2f(m1 * LOG2E - ms1);
-        m0 = mn0; m1 = mn1;
-        l0 *= a0; l1 *= a1;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
-        uint32_t pf[4][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float p0 = exp2f(s[j][0] * LOG2E - ms0), p1 = exp2f(s[j][1] * LOG2E - ms0);
-          const float p2 = exp2f(s[j][2] * LOG2E - ms1), p3 = exp2f(s[j][3] * LOG2E - ms1);
-          l0 += p0 + p1; l1 += p2 + p3;
-          pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
-          pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-        }
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          if (kk < npairs) {
-            const uint32_t vb = sm.v + (k0 + 16 * kk) * ROW_BYTES;
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-              uint32_t bf[4];
-              ldsm_x4_t(vb + fo.a[dp], bf);
-              mma_bf16(o[2 * dp], pf[kk], bf[0], bf[1]);
-              mma_bf16(o[2 * dp + 1], pf[kk], bf[2], bf[3]);
-            }
-          }
-        }
+    for (int ci = 0; get_chunk<TIME, NWARPS, 4>(c, G.T, r0, part, ci, ch); ++ci) {
+      switch (ch.np) {
+        case 4: fwd_chunk<TIME, 4>(c, sm, fo, ch, qf, rowA, rowB, t, m0, m1, l0, l1, o); break;
+        case 3: fwd_chunk<TIME, 3>(c, sm, fo, ch, qf, rowA, rowB, t, m0, m1, l0, l1, o); break;
+        case 2: fwd_chunk<TIME, 2>(c, sm, fo, ch, qf, rowA, rowB, t, m0, m1, l0, l1, o); break;
+        default: fwd_chunk<TIME, 1>(c, sm, fo, ch, qf, rowA, rowB, t, m0, m1, l0, l1, o); break;
       }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     {
-      const int rc = NP - r0;   // local index of the CLS row in this tile, if any
+      const int rc = c.NP - r0;   // local index of the CLS row in this tile, if any
       if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
         const bool hi_half = rc >= 8;
         constexpr int PARTS = TIME ? NWARPS : 1;
-        float* dst = cls_part + ((((long long)(b * G.H + h)) * G.G + g) * PARTS + part) * 66;
+        float* dst = cls_part + ((((long long)(b * G.H + h)) * G.G + g) * PARTS + max(part, 0)) * 66;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           dst[j * 8 + 2 * t] = hi_half ? o[j][2] : o[j][0];
@@ -804,7 +814,7 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
         if (t == 0) { dst[64] = hi_half ? m1 : m0; dst[65] = hi_half ? l1 : l0; }
       }
     }
-    if (TIME && r0 == NP) continue;     // a CLS part: nothing else to store
+    if (part >= 0) continue;     // a CLS part: nothing else to store
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     if (t == 0) {
       const int tok0 = row_token(G, g, rowA), tok1 = row_token(G, g, rowB);
@@ -812,6 +822,126 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
       if (tok1 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok1] = m1 + logf(l1);
     }
     store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
+  }
+}
+
+// ---- backward, phase 1 chunk: rows = queries (tile r0), pairs = keys.  dQ += (P o (dP - delta)) K
+template <bool TIME, int NPR>
+__device__ __forceinline__ void bwd_q_chunk(const FastCtx& c, const Smem& sm, const FragOff& fo, const Chunk& ch, int r0,
+                                            int rowA, int rowB, int t, float ls0, float ls1, float de0, float de1,
+                                            float (&dq)[8][4]) {
+  float s[2 * NPR][4], dp[2 * NPR][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NPR; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t aq[4], ad[4];          // A fragments re-read per chunk: registers limit CTAs per SM here
+    ldsm_x4(sm.q + r0 * ROW_BYTES + fo.a[kk], aq);
+    ldsm_x4(sm.dout + r0 * ROW_BYTES + fo.a[kk], ad);
+#pragma unroll
+    for (int p = 0; p < NPR; ++p) {
+      uint32_t bf[4];
+      ldsm_x4(sm.k + ch.base[p] * ROW_BYTES + fo.b[kk], bf);
+      mma_bf16(s[2 * p], aq, bf[0], bf[1]);
+      mma_bf16(s[2 * p + 1], aq, bf[2], bf[3]);
+      ldsm_x4(sm.v + ch.base[p] * ROW_BYTES + fo.b[kk], bf);
+      mma_bf16(dp[2 * p], ad, bf[0], bf[1]);
+      mma_bf16(dp[2 * p + 1], ad, bf[2], bf[3]);
+    }
+  }
+  uint32_t dsf[NPR][4];
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const bool masked = ch.mask & (1u << p);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;
+      bool v0 = true, v1 = true, v2 = true, v3 = true;
+      if (masked) {
+        v0 = fast_valid<TIME>(c, rowA, col); v1 = fast_valid<TIME>(c, rowA, col + 1);
+        v2 = fast_valid<TIME>(c, rowB, col); v3 = fast_valid<TIME>(c, rowB, col + 1);
+      }
+      const float p0 = v0 ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
+      const float p1 = v1 ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
+      const float p2 = v2 ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
+      const float p3 = v3 ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
+      dsf[p][jj * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
+      dsf[p][jj * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const uint32_t kb = sm.k + ch.base[p] * ROW_BYTES;
+#pragma unroll
+    for (int dpi = 0; dpi < 4; ++dpi) {
+      uint32_t bf[4];
+      ldsm_x4_t(kb + fo.a[dpi], bf);
+      mma_bf16(dq[2 * dpi], dsf[p], bf[0], bf[1]);
+      mma_bf16(dq[2 * dpi + 1], dsf[p], bf[2], bf[3]);
+    }
+  }
+}
+
+// ---- backward, phase 2 chunk: rows = keys (tile k0r), pairs = queries.  dV += P^T dO, dK += dS^T Q
+template <bool TIME, int NPR>
+__device__ __forceinline__ void bwd_k_chunk(const FastCtx& c, const Smem& sm, const FragOff& fo, const Chunk& ch, int k0r,
+                                            int keyA, int keyB, int t, float (&dk)[8][4], float (&dv)[8][4]) {
+  float st[2 * NPR][4], dpt[2 * NPR][4];
+#pragma unroll
+  for (int j = 0; j < 2 * NPR; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t ak[4], av[4];
+    ldsm_x4(sm.k + k0r * ROW_BYTES + fo.a[kk], ak);
+    ldsm_x4(sm.v + k0r * ROW_BYTES + fo.a[kk], av);
+#pragma unroll
+    for (int p = 0; p < NPR; ++p) {
+      uint32_t bf[4];
+      ldsm_x4(sm.q + ch.base[p] * ROW_BYTES + fo.b[kk], bf);
+      mma_bf16(st[2 * p], ak, bf[0], bf[1]);
+      mma_bf16(st[2 * p + 1], ak, bf[2], bf[3]);
+      ldsm_x4(sm.dout + ch.base[p] * ROW_BYTES + fo.b[kk], bf);
+      mma_bf16(dpt[2 * p], av, bf[0], bf[1]);
+      mma_bf16(dpt[2 * p + 1], av, bf[2], bf[3]);
+    }
+  }
+  uint32_t pf[NPR][4], dsf[NPR][4];
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const bool masked = ch.mask & (1u << p);
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;       // query index
+      bool v0 = true, v1 = true, v2 = true, v3 = true;
+      if (masked) {
+        v0 = fast_valid<TIME>(c, col, keyA); v1 = fast_valid<TIME>(c, col + 1, keyA);
+        v2 = fast_valid<TIME>(c, col, keyB); v3 = fast_valid<TIME>(c, col + 1, keyB);
+      }
+      const float2 lq = *reinterpret_cast<const float2*>(sm.lse + col);
+      const float2 dq2 = *reinterpret_cast<const float2*>(sm.delta + col);
+      const float p0 = v0 ? exp2f(st[j][0] * LOG2E - lq.x) : 0.f;
+      const float p1 = v1 ? exp2f(st[j][1] * LOG2E - lq.y) : 0.f;
+      const float p2 = v2 ? exp2f(st[j][2] * LOG2E - lq.x) : 0.f;
+      const float p3 = v3 ? exp2f(st[j][3] * LOG2E - lq.y) : 0.f;
+      pf[p][jj * 2] = pack_bf16x2(p0, p1);
+      pf[p][jj * 2 + 1] = pack_bf16x2(p2, p3);
+      dsf[p][jj * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq2.x), p1 * (dpt[j][1] - dq2.y));
+      dsf[p][jj * 2 + 1] = pack_bf16x2(p2 * (dpt[j][2] - dq2.x), p3 * (dpt[j][3] - dq2.y));
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < NPR; ++p) {
+    const uint32_t qb = sm.q + ch.base[p] * ROW_BYTES, db = sm.dout + ch.base[p] * ROW_BYTES;
+#pragma unroll
+    for (int dpi = 0; dpi < 4; ++dpi) {
+      uint32_t bf[4];
+      ldsm_x4_t(db + fo.a[dpi], bf);
+      mma_bf16(dv[2 * dpi], pf[p], bf[0], bf[1]);
+      mma_bf16(dv[2 * dpi + 1], pf[p], bf[2], bf[3]);
+      ldsm_x4_t(qb + fo.a[dpi], bf);
+      mma_bf16(dk[2 * dpi], dsf[p], bf[0], bf[1]);
+      mma_bf16(dk[2 * dpi + 1], dsf[p], bf[2], bf[3]);
+    }
   }
 }
 
@@ -831,18 +961,18 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
-  const bool first_group = (g == 0);
-  const int NP = G.NP;
-  const int valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : NP;
+  FastCtx c;
+  c.NP = G.NP; c.NPAD = G.NPAD; c.sh = sh; c.first_group = (g == 0);
+  c.valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : G.NP;
   const FragOff fo = make_frag_off(lane);
 
   // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row
   for (int r = warp * 4 + (lane >> 3); r < G.NPAD; r += NWARPS * 4) {
-    const int tok = row_token(G, g, r), c = lane & 7;
+    const int tok = row_token(G, g, r), cc = lane & 7;
     float d = 0.f;
     if (tok >= 0) {
-      const uint4 ov = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + c * 8);
-      const uint4 dv = *reinterpret_cast<const uint4*>(smem_gen + (sw_addr(sm.dout, r, c) - smem_base));
+      const uint4 ov = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + cc * 8);
+      const uint4 dv = *reinterpret_cast<const uint4*>(smem_gen + (sw_addr(sm.dout, r, cc) - smem_base));
       const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -851,7 +981,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
     }
     d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
-    if (c == 0) {
+    if (cc == 0) {
       sm.delta[r] = d;
       sm.lse[r] = tok >= 0 ? lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E : 0.f;
     }
@@ -861,74 +991,20 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   // phase 1: per 16 query rows -> dQ
   for (int it = warp;; it += NWARPS) {
     int r0, part;
-    Spans sp;
-    if (!work_item<TIME, NWARPS>(G, it, valid_keys, r0, part, sp)) break;
+    if (!work_item<TIME, NWARPS>(c, it, r0, part)) break;
     const int rowA = r0 + gq, rowB = rowA + 8;
     const float ls0 = sm.lse[rowA], ls1 = sm.lse[rowB], de0 = sm.delta[rowA], de1 = sm.delta[rowB];
     float dq[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.f; }
+    Chunk ch;
 #pragma unroll 1
-    for (int si = 0; si < 2; ++si) {
-#pragma unroll 1
-      for (int k0 = sp.lo[si]; k0 < sp.hi[si]; k0 += 32) {
-        const int npairs = min(2, (sp.hi[si] - k0) >> 4);
-        float s[4][4], dp[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.f; }
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          if (p < npairs) {
-            const uint32_t kb = sm.k + (k0 + 16 * p) * ROW_BYTES, vb = sm.v + (k0 + 16 * p) * ROW_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              uint32_t af[4], bf[4];
-              ldsm_x4(sm.q + r0 * ROW_BYTES + fo.a[kk], af);
-              ldsm_x4(kb + fo.b[kk], bf);
-              mma_bf16(s[2 * p], af, bf[0], bf[1]);
-              mma_bf16(s[2 * p + 1], af, bf[2], bf[3]);
-              ldsm_x4(sm.dout + r0 * ROW_BYTES + fo.a[kk], af);
-              ldsm_x4(vb + fo.b[kk], bf);
-              mma_bf16(dp[2 * p], af, bf[0], bf[1]);
-              mma_bf16(dp[2 * p + 1], af, bf[2], bf[3]);
-            }
-          }
-        }
-        uint32_t dsf[2][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = k0 + 8 * j + 2 * t;
-          bool v0 = j < 2 * npairs, v1 = v0, v2 = v0, v3 = v0;
-          if (sp.mask[si]) {
-            v0 = v0 && fast_valid<TIME>(rowA, col, NP, sh, valid_keys, first_group);
-            v1 = v1 && fast_valid<TIME>(rowA, col + 1, NP, sh, valid_keys, first_group);
-            v2 = v2 && fast_valid<TIME>(rowB, col, NP, sh, valid_keys, first_group);
-            v3 = v3 && fast_valid<TIME>(rowB, col + 1, NP, sh, valid_keys, first_group);
-          }
-          const float p0 = v0 ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
-          const float p1 = v1 ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
-          const float p2 = v2 ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
-          const float p3 = v3 ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
-          dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
-          dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
-        }
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          if (kk < npairs) {
-            const uint32_t kb = sm.k + (k0 + 16 * kk) * ROW_BYTES;
-#pragma unroll
-            for (int dpi = 0; dpi < 4; ++dpi) {
-              uint32_t bf[4];
-              ldsm_x4_t(kb + fo.a[dpi], bf);
-              mma_bf16(dq[2 * dpi], dsf[kk], bf[0], bf[1]);
-              mma_bf16(dq[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
-            }
-          }
-        }
-      }
+    for (int ci = 0; get_chunk<TIME, NWARPS, 2>(c, G.T, r0, part, ci, ch); ++ci) {
+      if (ch.np == 2) bwd_q_chunk<TIME, 2>(c, sm, fo, ch, r0, rowA, rowB, t, ls0, ls1, de0, de1, dq);
+      else bwd_q_chunk<TIME, 1>(c, sm, fo, ch, r0, rowA, rowB, t, ls0, ls1, de0, de1, dq);
     }
     {
-      const int rc = NP - r0;
+      const int rc = c.NP - r0;
       if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
         const bool hi_half = rc >= 8;
         float* dst = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD;
@@ -939,86 +1015,25 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
       }
     }
-    store_frag_rows_bf16(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane);
+    if (part < 0) store_frag_rows_bf16(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane);
   }
 
-  // phase 2: per 16 keys -> dK, dV   (tile rows = keys, columns = queries)
+  // phase 2: per 16 keys -> dK, dV   (tile rows = keys, pairs = queries)
   for (int it = warp;; it += NWARPS) {
     int k0r, part;
-    Spans sp;
-    if (!work_item<TIME, NWARPS>(G, it, valid_keys, k0r, part, sp)) break;
+    if (!work_item<TIME, NWARPS>(c, it, k0r, part)) break;
     const int keyA = k0r + gq, keyB = keyA + 8;
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.f; dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.f; }
+    Chunk ch;
 #pragma unroll 1
-    for (int si = 0; si < 2; ++si) {
-#pragma unroll 1
-      for (int q0 = sp.lo[si]; q0 < sp.hi[si]; q0 += 32) {
-        const int npairs = min(2, (sp.hi[si] - q0) >> 4);
-        float st[4][4], dpt[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.f; dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.f; }
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          if (p < npairs) {
-            const uint32_t qb = sm.q + (q0 + 16 * p) * ROW_BYTES, db = sm.dout + (q0 + 16 * p) * ROW_BYTES;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              uint32_t af[4], bf[4];
-              ldsm_x4(sm.k + k0r * ROW_BYTES + fo.a[kk], af);
-              ldsm_x4(qb + fo.b[kk], bf);
-              mma_bf16(st[2 * p], af, bf[0], bf[1]);
-              mma_bf16(st[2 * p + 1], af, bf[2], bf[3]);
-              ldsm_x4(sm.v + k0r * ROW_BYTES + fo.a[kk], af);
-              ldsm_x4(db + fo.b[kk], bf);
-              mma_bf16(dpt[2 * p], af, bf[0], bf[1]);
-              mma_bf16(dpt[2 * p + 1], af, bf[2], bf[3]);
-            }
-          }
-        }
-        uint32_t pf[2][4], dsf[2][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int col = q0 + 8 * j + 2 * t;       // query index
-          bool v0 = j < 2 * npairs, v1 = v0, v2 = v0, v3 = v0;
-          if (sp.mask[si]) {
-            v0 = v0 && fast_valid<TIME>(col, keyA, NP, sh, valid_keys, first_group);
-            v1 = v1 && fast_valid<TIME>(col + 1, keyA, NP, sh, valid_keys, first_group);
-            v2 = v2 && fast_valid<TIME>(col, keyB, NP, sh, valid_keys, first_group);
-            v3 = v3 && fast_valid<TIME>(col + 1, keyB, NP, sh, valid_keys, first_group);
-          }
-          const float2 lq = *reinterpret_cast<const float2*>(sm.lse + col);
-          const float2 dq2 = *reinterpret_cast<const float2*>(sm.delta + col);
-          const float p0 = v0 ? exp2f(st[j][0] * LOG2E - lq.x) : 0.f;
-          const float p1 = v1 ? exp2f(st[j][1] * LOG2E - lq.y) : 0.f;
-          const float p2 = v2 ? exp2f(st[j][2] * LOG2E - lq.x) : 0.f;
-          const float p3 = v3 ? exp2f(st[j][3] * LOG2E - lq.y) : 0.f;
-          pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
-          pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-          dsf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq2.x), p1 * (dpt[j][1] - dq2.y));
-          dsf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2 * (dpt[j][2] - dq2.x), p3 * (dpt[j][3] - dq2.y));
-        }
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          if (kk < npairs) {
-            const uint32_t qb = sm.q + (q0 + 16 * kk) * ROW_BYTES, db = sm.dout + (q0 + 16 * kk) * ROW_BYTES;
-#pragma unroll
-            for (int dpi = 0; dpi < 4; ++dpi) {
-              uint32_t bf[4];
-              ldsm_x4_t(db + fo.a[dpi], bf);
-              mma_bf16(dv[2 * dpi], pf[kk], bf[0], bf[1]);
-              mma_bf16(dv[2 * dpi + 1], pf[kk], bf[2], bf[3]);
-              ldsm_x4_t(qb + fo.a[dpi], bf);
-              mma_bf16(dk[2 * dpi], dsf[kk], bf[0], bf[1]);
-              mma_bf16(dk[2 * dpi + 1], dsf[kk], bf[2], bf[3]);
-            }
-          }
-        }
-      }
+    for (int ci = 0; get_chunk<TIME, NWARPS, 2>(c, G.T, k0r, part, ci, ch); ++ci) {
+      if (ch.np == 2) bwd_k_chunk<TIME, 2>(c, sm, fo, ch, k0r, keyA, keyB, t, dk, dv);
+      else bwd_k_chunk<TIME, 1>(c, sm, fo, ch, k0r, keyA, keyB, t, dk, dv);
     }
     {
-      const int rc = NP - k0r;
+      const int rc = c.NP - k0r;
       if (rc >= 0 && rc < 16 && (rc & 7) == gq) {
         const bool hi_half = rc >= 8;
         float* dstk = dcls + ((long long)(b * G.H + h) * 3 + 1) * HD;
@@ -1032,8 +1047,10 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
       }
     }
-    store_frag_rows_bf16(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane);
-    store_frag_rows_bf16(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane);
+    if (part < 0) {
+      store_frag_rows_bf16(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane);
+      store_frag_rows_bf16(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane);
+    }
   }
 }
 
