@@ -65,22 +65,37 @@ layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __
   }
 }
 
-template <int NV, bool DY16>
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)   // <=128 registers: 16 warps / SM keep enough loads in flight
-layernorm_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* __restrict__ x, long long ldx,
+// Backward.  4 warps / CTA, one row per warp iteration.  The d(gamma) / d(beta) partial sums live in warp-private
+// shared memory (each lane owns fixed float4 slots, so no synchronisation) instead of 48 registers: that brings
+// the kernel to <= 80 registers and 6 CTAs (24 warps) per SM, which is what a pure streaming kernel needs.
+constexpr int LNB_WARPS = 4;
+
+__device__ __forceinline__ float4 load4_f32_or_bf16(const void* p, bool is16, long long off) {
+  if (is16) {
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + off);
+    const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 6)
+layernorm_bwd_kernel(const void* __restrict__ dy_, int dy16, long long lddy, const float* __restrict__ x, long long ldx,
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-                     const float* __restrict__ add1, const float* __restrict__ add2, float* __restrict__ dx,
-                     long long lddx, bf16* __restrict__ dx16, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                     int rows, int D) {
-  __shared__ float red[LN_WARPS][NV * 128 + 4];
+                     const void* __restrict__ add1, int add1_16, const void* __restrict__ add2, int add2_16,
+                     float* __restrict__ dx, long long lddx, bf16* __restrict__ dx16, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int rows, int D) {
+  __shared__ float4 acc_g[LNB_WARPS][NV * 32];
+  __shared__ float4 acc_b[LNB_WARPS][NV * 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4 pg[NV], pb[NV];
+  const bool want_param_grads = dgamma != nullptr || dbeta != nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    pg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    pb[i] = pg[i];
+    acc_g[warp][i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_b[warp][i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = blockIdx.x * LN_WARPS + warp; row < rows; row += gridDim.x * LN_WARPS) {
+  for (int row = blockIdx.x * LNB_WARPS + warp; row < rows; row += gridDim.x * LNB_WARPS) {
     const float mu = mean[row], rs = rstd[row];
     float4 dyv[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
@@ -88,18 +103,23 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* 
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < D) {
-        if (DY16) {
-          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(dy_) + (long long)row * lddy + c);
-          const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
-          dyv[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
-        } else {
-          dyv[i] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (long long)row * lddy + c);
-        }
+        dyv[i] = load4_f32_or_bf16(dy_, dy16, (long long)row * lddy + c);
         const float4 xv = *reinterpret_cast<const float4*>(x + (long long)row * ldx + c);
         xh[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        pg[i].x += dyv[i].x * xh[i].x; pg[i].y += dyv[i].y * xh[i].y; pg[i].z += dyv[i].z * xh[i].z; pg[i].w += dyv[i].w * xh[i].w;
-        pb[i].x += dyv[i].x; pb[i].y += dyv[i].y; pb[i].z += dyv[i].z; pb[i].w += dyv[i].w;
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));   // L1-resident, not worth 24 registers
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < D) {
+        if (want_param_grads) {
+          float4 ag = acc_g[warp][i * 32 + lane], ab = acc_b[warp][i * 32 + lane];
+          ag.x += dyv[i].x * xh[i].x; ag.y += dyv[i].y * xh[i].y; ag.z += dyv[i].z * xh[i].z; ag.w += dyv[i].w * xh[i].w;
+          ab.x += dyv[i].x; ab.y += dyv[i].y; ab.z += dyv[i].z; ab.w += dyv[i].w;
+          acc_g[warp][i * 32 + lane] = ag;
+          acc_b[warp][i * 32 + lane] = ab;
+        }
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
         dyv[i].x *= g4.x; dyv[i].y *= g4.y; dyv[i].z *= g4.z; dyv[i].w *= g4.w;
         s1 += dyv[i].x + dyv[i].y + dyv[i].z + dyv[i].w;
         s2 += dyv[i].x * xh[i].x + dyv[i].y * xh[i].y + dyv[i].z * xh[i].z + dyv[i].w * xh[i].w;
@@ -113,33 +133,23 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, long long lddy, const float* 
         float4 o = make_float4(rs * (dyv[i].x - c1 - xh[i].x * c2), rs * (dyv[i].y - c1 - xh[i].y * c2),
                                rs * (dyv[i].z - c1 - xh[i].z * c2), rs * (dyv[i].w - c1 - xh[i].w * c2));
         const long long off = (long long)row * D + c;
-        if (add1) { const float4 a = *reinterpret_cast<const float4*>(add1 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
-        if (add2) { const float4 a = *reinterpret_cast<const float4*>(add2 + off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (add1) { const float4 a = load4_f32_or_bf16(add1, add1_16, off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (add2) { const float4 a = load4_f32_or_bf16(add2, add2_16, off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         if (dx) *reinterpret_cast<float4*>(dx + (long long)row * lddx + c) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
-  if (!dgamma && !dbeta) return;
-  // block reduce the per-warp partial dgamma / dbeta, then one atomicAdd per column per block
-  for (int pass = 0; pass < 2; ++pass) {
-    __syncthreads();
+  if (!want_param_grads) return;
+  __syncthreads();
+  const float* fg = reinterpret_cast<const float*>(&acc_g[0][0]);
+  const float* fb = reinterpret_cast<const float*>(&acc_b[0][0]);
+  for (int c = threadIdx.x; c < D; c += LNB_WARPS * 32) {
+    float sg = 0.f, sb = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      const float4 p = pass == 0 ? pg[i] : pb[i];
-      red[warp][c] = p.x; red[warp][c + 1] = p.y; red[warp][c + 2] = p.z; red[warp][c + 3] = p.w;
-    }
-    __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (dst) {
-      for (int c = threadIdx.x; c < D; c += LN_WARPS * 32) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) s += red[w][c];
-        atomicAdd(dst + c, s);
-      }
-    }
+    for (int w = 0; w < LNB_WARPS; ++w) { sg += fg[w * NV * 128 + c]; sb += fb[w * NV * 128 + c]; }
+    if (dgamma) atomicAdd(dgamma + c, sg);
+    if (dbeta) atomicAdd(dbeta + c, sb);
   }
 }
 
@@ -211,17 +221,12 @@ int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_ou
 
 template <int NV>
 int launch_ln_bwd(const void* dy, int dy16, long long lddy, const float* x, long long ldx, const float* gamma,
-                  const float* mean, const float* rstd, const float* add1, const float* add2, float* dx, long long lddx,
-                  void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 8);
-  if (dy16)
-    layernorm_bwd_kernel<NV, true><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
-                                                                  lddx, reinterpret_cast<bf16*>(dx16), dgamma, dbeta,
-                                                                  rows, D);
-  else
-    layernorm_bwd_kernel<NV, false><<<grid, LN_WARPS * 32, 0, st>>>(dy, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx,
-                                                                   lddx, reinterpret_cast<bf16*>(dx16), dgamma, dbeta,
-                                                                   rows, D);
+                  const float* mean, const float* rstd, const void* add1, int add1_16, const void* add2, int add2_16,
+                  float* dx, long long lddx, void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
+  const int grid = min((rows + LNB_WARPS - 1) / LNB_WARPS, num_sms() * 12);
+  layernorm_bwd_kernel<NV><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy16, lddy, x, ldx, gamma, mean, rstd, add1, add1_16, add2,
+                                                           add2_16, dx, lddx, reinterpret_cast<bf16*>(dx16), dgamma,
+                                                           dbeta, rows, D);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
@@ -246,15 +251,15 @@ extern "C" int egovlp_layernorm_fwd(const float* x, long long ldx, const float* 
 }
 
 extern "C" int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx,
-                                    const float* gamma, const float* mean, const float* rstd, const float* add1,
-                                    const float* add2, float* dx, long long lddx, void* dx_bf16, float* dgamma,
-                                    float* dbeta, int rows, int D, void* stream) {
+                                    const float* gamma, const float* mean, const float* rstd, const void* add1,
+                                    int add1_is_bf16, const void* add2, int add2_is_bf16, float* dx, long long lddx,
+                                    void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream) {
   EGOVLP_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_bf16), "layernorm_bwd: null pointer");
   EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "layernorm_bwd: bad D=%d", D);
   if (rows == 0) return EGOVLP_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (D + 127) / 128;
-#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, dy_is_bf16, lddy, x, ldx, gamma, mean, rstd, add1, add2, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
+#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, dy_is_bf16, lddy, x, ldx, gamma, mean, rstd, add1, add1_is_bf16, add2, add2_is_bf16, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
   switch (nv) { LN_BWD_CASE(1); LN_BWD_CASE(2); LN_BWD_CASE(3); LN_BWD_CASE(4); LN_BWD_CASE(5); LN_BWD_CASE(6); LN_BWD_CASE(7); LN_BWD_CASE(8); }
 #undef LN_BWD_CASE
   return EGOVLP_ERR_UNSUPPORTED;

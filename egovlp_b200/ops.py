@@ -96,16 +96,19 @@ def layernorm_fwd(x, gamma, beta, eps, *, add=None, sum_out=None, y16=None, y32=
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx16=None, dgamma=None, dbeta=None):
+    """dx = LNbwd(dy) + add1 + add2.  dy / add1 / add2 may each be fp32 or bf16."""
     _chk(x, F32, "x")
     rows, D = x.shape
     assert dy.is_cuda and dy.dtype in (F32, BF16) and dy.shape == (rows, D) and dy.stride(1) == 1 and x.stride(1) == 1
     for t in (add1, add2):
-        assert t is None or (t.dtype == F32 and t.is_contiguous() and t.shape == (rows, D))
+        assert t is None or (t.dtype in (F32, BF16) and t.is_contiguous() and t.shape == (rows, D))
     assert dx is None or (dx.dtype == F32 and dx.shape == (rows, D) and dx.stride(1) == 1)
     assert dx16 is None or (dx16.dtype == BF16 and dx16.is_contiguous() and dx16.shape == (rows, D))
-    call("egovlp_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), C.c_longlong(dy.stride(0)), _ptr(x), C.c_longlong(x.stride(0)),
-         _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1), _ptr(add2), _ptr(dx),
-         C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, D, _stream())
+    call("egovlp_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), C.c_longlong(dy.stride(0)), _ptr(x),
+         C.c_longlong(x.stride(0)), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1),
+         int(add1 is not None and add1.dtype == BF16), _ptr(add2), int(add2 is not None and add2.dtype == BF16),
+         _ptr(dx), C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, D,
+         _stream())
 
 
 def cast_bf16(src, dst=None):

@@ -75,10 +75,12 @@ int egovlp_layernorm_fwd(const float* x, long long ldx, const float* add, float*
 /* Backward.  dx = LNbwd(dy) [+ add1] [+ add2]  (fp32 [rows, D], row stride lddx), optionally also stored as bf16
  * (dx_bf16, row stride D) for use as a GEMM operand.  add1/add2 carry the residual-stream gradients that bypass the LN
  * (SpaceTimeBlock: dsr = dy + LN2bwd, dx = dsr + dtr + LN3bwd).  dgamma/dbeta (fp32 [D]) are ACCUMULATED
- * with atomicAdd -- zero them first for a plain gradient; either may be NULL.  dy is fp32 or bf16 (dy_is_bf16). */
-int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx, const float* gamma,
-                         const float* mean, const float* rstd, const float* add1, const float* add2, float* dx,
-                         long long lddx, void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream);
+ * with atomicAdd -- zero them first for a plain gradient; either may be NULL.  dy, add1 and add2 are each fp32 or
+ * bf16 (the *_is_bf16 flags; add rows are dense, stride D). */
+int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx,
+                         const float* gamma, const float* mean, const float* rstd, const void* add1, int add1_is_bf16,
+                         const void* add2, int add2_is_bf16, float* dx, long long lddx, void* dx_bf16, float* dgamma,
+                         float* dbeta, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Divided space-time attention core of VarAttention.forward (model/video_transformer.py:104-133) and its

@@ -126,6 +126,12 @@ def test_layernorm_fwd_bwd(ops, rows, D):
     ref2.backward(dy16.float())
     ops.layernorm_bwd(dy16, x, g, mean, rstd, dx=dx)
     assert rel_err(dx, xr2.grad) < 1e-5
+    # bf16 residual-gradient addends (block-internal d space/time residual)
+    a1h, a2h = a1.to(torch.bfloat16), a2.to(torch.bfloat16)
+    ops.layernorm_bwd(dy16, x, g, mean, rstd, add1=a1h, add2=a2h, dx=dx, dx16=dx16)
+    assert rel_err(dx, xr2.grad + a1h.float() + a2h.float()) < 1e-5
+    ops.layernorm_bwd(dy16, x, g, mean, rstd, add1=a1, add2=a2h, dx16=dx16)          # mixed dtypes, bf16-only output
+    assert rel_err(dx16, xr2.grad + a1 + a2h.float()) < 4e-3
 
 
 def test_layernorm_fused_add(ops):
