@@ -128,7 +128,8 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
 // Same, straight from the fragments (each quad writes 16 contiguous bytes of a row): used by the backward, whose
 // four resident tiles leave no room for staging when two CTAs share an SM.
 __device__ __forceinline__ void store_frag_rows_bf16(const float (&acc)[8][4], float s, bf16* dst, long long ld, int col0,
-                                                     const Geom& G, int b, int g, int r0, int lane) {
+                                                     const Geom& G, int b, int g, int r0, int lane, float s_hi = -1.f) {
+  const float sB = s_hi >= 0.f ? s_hi : s;   // optional separate scale for the rows g+8
   const int gq = lane >> 2, t = lane & 3;
   const int tok0 = row_token(G, g, r0 + gq), tok1 = row_token(G, g, r0 + gq + 8);
   bf16* p0 = dst + ((long long)b * G.S + tok0) * ld + col0 + 2 * t;
@@ -136,7 +137,7 @@ __device__ __forceinline__ void store_frag_rows_bf16(const float (&acc)[8][4], f
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (tok0 > 0) *reinterpret_cast<uint32_t*>(p0 + 8 * j) = pack_bf16x2(acc[j][0] * s, acc[j][1] * s);
-    if (tok1 > 0) *reinterpret_cast<uint32_t*>(p1 + 8 * j) = pack_bf16x2(acc[j][2] * s, acc[j][3] * s);
+    if (tok1 > 0) *reinterpret_cast<uint32_t*>(p1 + 8 * j) = pack_bf16x2(acc[j][2] * sB, acc[j][3] * sB);
   }
 }
 
@@ -155,7 +156,7 @@ __device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int&
 }
 
 // Shared prologue: carve smem, gather the group's tiles (TMA) + CLS rows (manual), build the gid table.
-template <bool BWD>
+template <bool BWD, bool STAGE = !BWD>
 __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_qkv, const CUtensorMap* tm_do,
                                            const bf16* qkv, const bf16* dout, int b, int h, int g, uint8_t* smem_gen,
                                            uint32_t smem_base, Smem& sm, int nwarps) {
@@ -166,7 +167,7 @@ __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_
   sm.dout = sm.v + tile_bytes;
   uint32_t off = (BWD ? 4 : 3) * tile_bytes;
   sm.stage = smem_base + off;
-  if (!BWD) off += nwarps * 16 * ROW_BYTES;
+  if (STAGE) off += nwarps * 16 * ROW_BYTES;
   sm.lse = reinterpret_cast<float*>(smem_gen + off);
   off += G.NPAD * 4;
   sm.delta = reinterpret_cast<float*>(smem_gen + off);
@@ -766,7 +767,7 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
   int b, h, g;
   decode_block(G, b, h, g);
   Smem sm;
-  load_group<false>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  load_group<false, !TIME>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -821,7 +822,8 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
       if (tok0 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok0] = m0 + logf(l0);
       if (tok1 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok1] = m1 + logf(l1);
     }
-    store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
+    if (TIME) store_frag_rows_bf16(o, i0, out, G.D, h * HD, G, b, g, r0, lane, i1);   // no staging: 4 CTAs / SM
+    else store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
   }
 }
 
@@ -1087,8 +1089,8 @@ int make_group_tmap(CUtensorMap* tm, const void* base, const Geom& G, int ncolbl
   return make_tmap_nd_bf16(tm, reinterpret_cast<const bf16*>(base) + W, 5, dims, strides, box, true);
 }
 
-size_t attn_smem_bytes(const Geom& G, bool bwd, int nwarps) {
-  return (size_t)(bwd ? 4 : 3) * G.NPAD * ROW_BYTES + (bwd ? 0 : nwarps * 16 * ROW_BYTES) + 2 * G.NPAD * 4 +
+size_t attn_smem_bytes(const Geom& G, bool bwd, int nwarps, bool staging = true) {
+  return (size_t)(bwd ? 4 : 3) * G.NPAD * ROW_BYTES + ((bwd || !staging) ? 0 : nwarps * 16 * ROW_BYTES) + 2 * G.NPAD * 4 +
          ((G.NPAD * 2 + 15) / 16) * 16 + 16 + 1024;
 }
 
@@ -1119,7 +1121,7 @@ extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, f
   const int grid = B * H * G.G;
 #define LAUNCH_FWD(KERN, W, ...)                                                                              \
   do {                                                                                                        \
-    const size_t smem = attn_smem_bytes(G, false, W);                                                         \
+    const size_t smem = attn_smem_bytes(G, false, W, generic || mode == 1);                                   \
     EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     KERN<<<grid, W * 32, smem, st>>>(tm, q, o, lse, cls_part, G, ##__VA_ARGS__);                              \
   } while (0)
@@ -1130,8 +1132,8 @@ extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, f
   } else if (mode == 1) {     // space: 13 row tiles over 7 warps, 2 CTAs / SM at 196 patches
     if (G.NPAD > 128) LAUNCH_FWD((fast_attn_fwd_kernel<false, 7, 2>), 7, 0);
     else LAUNCH_FWD((fast_attn_fwd_kernel<false, 4, 3>), 4, 0);
-  } else {                    // time: 8 row tiles over 4 warps, 3 CTAs / SM
-    LAUNCH_FWD((fast_attn_fwd_kernel<true, 4, 3>), 4, time_shift(G));
+  } else {                    // time: 7 patch tiles + 4 CLS parts over 4 warps, 4 CTAs / SM (no staging)
+    LAUNCH_FWD((fast_attn_fwd_kernel<true, 4, 4>), 4, time_shift(G));
   }
 #undef LAUNCH_FWD
   EGOVLP_CHECK_LAUNCH();

@@ -41,6 +41,7 @@ struct EpiParams {
   float col_scale;
   int col_scale_ncols;
   int res_row_mod;  // 0: residual row = m; else residual row = m % res_row_mod (broadcast table)
+  float* colsum;    // optional fp32 [N]: accumulates the column sums of the stored values (bias gradient)
 };
 
 template <int BLOCK_N>
@@ -272,7 +273,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
-        const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2;
+        const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.colsum != nullptr;
         if (!wide) {
           stage_bf16_rows(stg, lane, v);
           __syncwarp();
@@ -300,6 +301,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (ep.act == 2) auxv[i] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
           }
+          float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rl = 4 * i + (lane >> 3), grow = row0 + rl;
@@ -311,6 +313,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             }
             if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
             if (grow < M) {
+              cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
               if (ep.out_mode == 0) {
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (long long)grow * ep.ldo + col) =
                     make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
@@ -320,6 +323,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                 red_add_v4(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col, x.x, x.y, x.z, x.w);
               }
             }
+          }
+          if (ep.colsum) {     // lanes l, l+8, l+16, l+24 hold the same 4 columns: fold, then one vector atomic per column group
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
+            cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
+            cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
+            if (lane < 8) red_add_v4(ep.colsum + col, cs.x, cs.y, cs.z, cs.w);
           }
         }
         __syncwarp();   // staging buffer is reused by the next chunk
@@ -400,6 +410,7 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   ep.ldr = e->ldr; ep.ldaux = e->ldaux; ep.ldo = e->ldo; ep.ldo2 = e->ldo2;
   ep.out_mode = e->out_mode; ep.act = e->act; ep.alpha = e->alpha;
   ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols; ep.res_row_mod = e->res_row_mod;
+  ep.colsum = e->colsum;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (N % 256 == 0) return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
   return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);

@@ -85,15 +85,17 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, int dy16, long long lddy, con
                      const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                      const void* __restrict__ add1, int add1_16, const void* __restrict__ add2, int add2_16,
                      float* __restrict__ dx, long long lddx, bf16* __restrict__ dx16, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int rows, int D) {
+                     float* __restrict__ dbeta, float* __restrict__ colsum_dx, int rows, int D) {
   __shared__ float4 acc_g[LNB_WARPS][NV * 32];
   __shared__ float4 acc_b[LNB_WARPS][NV * 32];
+  __shared__ float4 acc_o[LNB_WARPS][NV * 32];   // column sums of the output (bias gradient of the producing Linear)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool want_param_grads = dgamma != nullptr || dbeta != nullptr;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     acc_g[warp][i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     acc_b[warp][i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_o[warp][i * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * LNB_WARPS + warp; row < rows; row += gridDim.x * LNB_WARPS) {
     const float mu = mean[row], rs = rstd[row];
@@ -135,21 +137,28 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, int dy16, long long lddy, con
         const long long off = (long long)row * D + c;
         if (add1) { const float4 a = load4_f32_or_bf16(add1, add1_16, off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
         if (add2) { const float4 a = load4_f32_or_bf16(add2, add2_16, off); o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w; }
+        if (colsum_dx) {
+          float4 ao = acc_o[warp][i * 32 + lane];
+          ao.x += o.x; ao.y += o.y; ao.z += o.z; ao.w += o.w;
+          acc_o[warp][i * 32 + lane] = ao;
+        }
         if (dx) *reinterpret_cast<float4*>(dx + (long long)row * lddx + c) = o;
         if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
       }
     }
   }
-  if (!want_param_grads) return;
+  if (!want_param_grads && !colsum_dx) return;
   __syncthreads();
   const float* fg = reinterpret_cast<const float*>(&acc_g[0][0]);
   const float* fb = reinterpret_cast<const float*>(&acc_b[0][0]);
+  const float* fo = reinterpret_cast<const float*>(&acc_o[0][0]);
   for (int c = threadIdx.x; c < D; c += LNB_WARPS * 32) {
-    float sg = 0.f, sb = 0.f;
+    float sg = 0.f, sb = 0.f, so = 0.f;
 #pragma unroll
-    for (int w = 0; w < LNB_WARPS; ++w) { sg += fg[w * NV * 128 + c]; sb += fb[w * NV * 128 + c]; }
+    for (int w = 0; w < LNB_WARPS; ++w) { sg += fg[w * NV * 128 + c]; sb += fb[w * NV * 128 + c]; so += fo[w * NV * 128 + c]; }
     if (dgamma) atomicAdd(dgamma + c, sg);
     if (dbeta) atomicAdd(dbeta + c, sb);
+    if (colsum_dx) atomicAdd(colsum_dx + c, so);
   }
 }
 
@@ -222,11 +231,12 @@ int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_ou
 template <int NV>
 int launch_ln_bwd(const void* dy, int dy16, long long lddy, const float* x, long long ldx, const float* gamma,
                   const float* mean, const float* rstd, const void* add1, int add1_16, const void* add2, int add2_16,
-                  float* dx, long long lddx, void* dx16, float* dgamma, float* dbeta, int rows, int D, cudaStream_t st) {
+                  float* dx, long long lddx, void* dx16, float* dgamma, float* dbeta, float* colsum_dx, int rows, int D,
+                  cudaStream_t st) {
   const int grid = min((rows + LNB_WARPS - 1) / LNB_WARPS, num_sms() * 12);
   layernorm_bwd_kernel<NV><<<grid, LNB_WARPS * 32, 0, st>>>(dy, dy16, lddy, x, ldx, gamma, mean, rstd, add1, add1_16, add2,
                                                            add2_16, dx, lddx, reinterpret_cast<bf16*>(dx16), dgamma,
-                                                           dbeta, rows, D);
+                                                           dbeta, colsum_dx, rows, D);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
@@ -253,13 +263,14 @@ extern "C" int egovlp_layernorm_fwd(const float* x, long long ldx, const float* 
 extern "C" int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx,
                                     const float* gamma, const float* mean, const float* rstd, const void* add1,
                                     int add1_is_bf16, const void* add2, int add2_is_bf16, float* dx, long long lddx,
-                                    void* dx_bf16, float* dgamma, float* dbeta, int rows, int D, void* stream) {
+                                    void* dx_bf16, float* dgamma, float* dbeta, float* colsum_dx, int rows, int D,
+                                    void* stream) {
   EGOVLP_CHECK_ARG(dy && x && gamma && mean && rstd && (dx || dx_bf16), "layernorm_bwd: null pointer");
   EGOVLP_CHECK_ARG(rows >= 0 && D > 0 && D % 4 == 0 && D <= 1024 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "layernorm_bwd: bad D=%d", D);
   if (rows == 0) return EGOVLP_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int nv = (D + 127) / 128;
-#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, dy_is_bf16, lddy, x, ldx, gamma, mean, rstd, add1, add1_is_bf16, add2, add2_is_bf16, dx, lddx, dx_bf16, dgamma, dbeta, rows, D, st)
+#define LN_BWD_CASE(n) case n: return launch_ln_bwd<n>(dy, dy_is_bf16, lddy, x, ldx, gamma, mean, rstd, add1, add1_is_bf16, add2, add2_is_bf16, dx, lddx, dx_bf16, dgamma, dbeta, colsum_dx, rows, D, st)
   switch (nv) { LN_BWD_CASE(1); LN_BWD_CASE(2); LN_BWD_CASE(3); LN_BWD_CASE(4); LN_BWD_CASE(5); LN_BWD_CASE(6); LN_BWD_CASE(7); LN_BWD_CASE(8); }
 #undef LN_BWD_CASE
   return EGOVLP_ERR_UNSUPPORTED;

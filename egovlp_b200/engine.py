@@ -190,36 +190,40 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         # ---- MLP:  y = sr + fc2(gelu(fc1(LN2(sr))))
         g_f2w, g_f2b = wgrad(dy16, h, D, HID), bgrad(dy)
         du = _empty((M, HID), BF16, dy)
-        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=2)               # (dy W2) * gelu'(u)
-        g_f1w, g_f1b = wgrad(du, n2, HID, D), bgrad(du)
+        g_f1b = _zeros((HID,), dy)
+        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=2, colsum=g_f1b)  # (dy W2) * gelu'(u); + bias grad
+        g_f1w = wgrad(du, n2, HID, D)
         dn2 = _empty((M, D), BF16, dy)                       # LayerNorm-input gradients travel as bf16
         ops.gemm(du, cache.get(f1w), dn2, b_mn=True)
         del du
         # gradients that stay inside the block (d space_residual, d time_residual) are kept in bf16 only
         dsr16 = _empty((M, D), BF16, dy)
         g_n2w, g_n2b = _zeros((D,), dy), _zeros((D,), dy)
-        ops.layernorm_bwd(dn2, sr, n2w.detach(), mean2, rstd2, add1=dy, dx16=dsr16, dgamma=g_n2w, dbeta=g_n2b)
+        g_spb = _zeros((D,), dy)                             # bias grad of attn.proj = colsum(d space_residual)
+        ops.layernorm_bwd(dn2, sr, n2w.detach(), mean2, rstd2, add1=dy, dx16=dsr16, dgamma=g_n2w, dbeta=g_n2b,
+                          colsum_dx=g_spb)
         del dn2
 
         def attention_bwd(dres16, qkv, a, lse, inp16, qw, pw, mode):
             dres = dres16
-            g_pw, g_pb = wgrad(dres16, a, D, D), bgrad(dres16)
+            g_pw = wgrad(dres16, a, D, D)
             da = _empty((M, D), BF16, dres)
             ops.gemm(dres16, cache.get(pw), da, b_mn=True)
             dqkv = ops.divided_attn_bwd(qkv, a, da, lse, B, T, N, H, mode, Q_SCALE)
             g_qw, g_qb = wgrad(dqkv, inp16, 3 * D, D), bgrad(dqkv)
             dinp = _empty((M, D), BF16, dres)
             ops.gemm(dqkv, cache.get(qw), dinp, b_mn=True)
-            return g_qw, g_qb, g_pw, g_pb, dinp
+            return g_qw, g_qb, g_pw, dinp
 
         # ---- space attention:  sr = x + proj(attn(LN1(tr)))
-        g_sqw, g_sqb, g_spw, g_spb, dn1 = attention_bwd(dsr16, qkv_s, a_s, lse_s, n1, sqw, spw, 1)
+        g_sqw, g_sqb, g_spw, dn1 = attention_bwd(dsr16, qkv_s, a_s, lse_s, n1, sqw, spw, 1)
         dtr16 = _empty((M, D), BF16, dy)
         g_n1w, g_n1b = _zeros((D,), dy), _zeros((D,), dy)
-        ops.layernorm_bwd(dn1, tr, n1w.detach(), mean1, rstd1, dx16=dtr16, dgamma=g_n1w, dbeta=g_n1b)
+        g_tpb = _zeros((D,), dy)                             # bias grad of timeattn.proj = colsum(d time_residual)
+        ops.layernorm_bwd(dn1, tr, n1w.detach(), mean1, rstd1, dx16=dtr16, dgamma=g_n1w, dbeta=g_n1b, colsum_dx=g_tpb)
         del dn1
         # ---- time attention:  tr = x + proj(timeattn(LN3(x)))
-        g_tqw, g_tqb, g_tpw, g_tpb, dn3 = attention_bwd(dtr16, qkv_t, a_t, lse_t, n3, tqw, tpw, 0)
+        g_tqw, g_tqb, g_tpw, dn3 = attention_bwd(dtr16, qkv_t, a_t, lse_t, n3, tqw, tpw, 0)
         dx, dx16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
         g_n3w, g_n3b = _zeros((D,), dy), _zeros((D,), dy)
         ops.layernorm_bwd(dn3, x2, n3w.detach(), mean3, rstd3, add1=dsr16, add2=dtr16, dx=dx, dx16=dx16, dgamma=g_n3w,

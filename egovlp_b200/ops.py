@@ -37,7 +37,7 @@ def profile_gemm(enable):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, out2=None, act=0, alpha=1.0,
-         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0):
+         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0, colsum=None):
     """out = epi(A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, last-dim contiguous.
     out: bf16 or fp32 [M,N]; accumulate=True -> fp32 atomic add into `out` (required for split_k>1)."""
     _chk(a, BF16, "a"); _chk(b, BF16, "b")
@@ -72,6 +72,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
         e.out_mode = 0 if out.dtype == BF16 else 1
     e.act, e.alpha, e.col_scale, e.col_scale_ncols = act, alpha, col_scale, col_scale_ncols
     e.res_row_mod = res_row_mod
+    if colsum is not None:
+        _chk(colsum, F32, "colsum"); assert colsum.numel() == N
+    e.colsum = colsum.data_ptr() if colsum is not None else None
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -95,7 +98,8 @@ def layernorm_fwd(x, gamma, beta, eps, *, add=None, sum_out=None, y16=None, y32=
          _ptr(beta), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), rows, D, C.c_float(eps), _stream())
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx16=None, dgamma=None, dbeta=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx16=None, dgamma=None, dbeta=None,
+                  colsum_dx=None):
     """dx = LNbwd(dy) + add1 + add2.  dy / add1 / add2 may each be fp32 or bf16."""
     _chk(x, F32, "x")
     rows, D = x.shape
@@ -107,7 +111,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx
     call("egovlp_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), C.c_longlong(dy.stride(0)), _ptr(x),
          C.c_longlong(x.stride(0)), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1),
          int(add1 is not None and add1.dtype == BF16), _ptr(add2), int(add2 is not None and add2.dtype == BF16),
-         _ptr(dx), C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta), rows, D,
+         _ptr(dx), C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
+         _ptr(colsum_dx), rows, D,
          _stream())
 
 

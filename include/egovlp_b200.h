@@ -57,6 +57,7 @@ typedef struct egovlp_gemm_epilogue {
   float col_scale;
   int col_scale_ncols;
   int res_row_mod; /* 0: residual row = m; >0: residual row = m % res_row_mod (broadcast [res_row_mod, ldr] table) */
+  float* colsum;   /* optional fp32 [N]: ACCUMULATES the column sums of the stored values (bias gradient of dy) */
 } egovlp_gemm_epilogue;
 
 int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,
@@ -76,11 +77,12 @@ int egovlp_layernorm_fwd(const float* x, long long ldx, const float* add, float*
  * (dx_bf16, row stride D) for use as a GEMM operand.  add1/add2 carry the residual-stream gradients that bypass the LN
  * (SpaceTimeBlock: dsr = dy + LN2bwd, dx = dsr + dtr + LN3bwd).  dgamma/dbeta (fp32 [D]) are ACCUMULATED
  * with atomicAdd -- zero them first for a plain gradient; either may be NULL.  dy, add1 and add2 are each fp32 or
- * bf16 (the *_is_bf16 flags; add rows are dense, stride D). */
+ * bf16 (the *_is_bf16 flags; add rows are dense, stride D).  colsum_dx (fp32 [D], optional) ACCUMULATES the
+ * column sums of the result: the bias gradient of the Linear that produced the normalised tensor's residual. */
 int egovlp_layernorm_bwd(const void* dy, int dy_is_bf16, long long lddy, const float* x, long long ldx,
                          const float* gamma, const float* mean, const float* rstd, const void* add1, int add1_is_bf16,
                          const void* add2, int add2_is_bf16, float* dx, long long lddx, void* dx_bf16, float* dgamma,
-                         float* dbeta, int rows, int D, void* stream);
+                         float* dbeta, float* colsum_dx, int rows, int D, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Divided space-time attention core of VarAttention.forward (model/video_transformer.py:104-133) and its

@@ -81,6 +81,12 @@ def test_gemm_epilogues(ops):
     x = aux.float().requires_grad_(True)
     torch.nn.functional.gelu(x).sum().backward()
     assert rel_err(out, (a.float() @ b.float().t()) * x.grad) < 1e-4
+    # same, bf16 output + fused column sums (the fc1 bias gradient)
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs = torch.ones(N, device="cuda")
+    ops.gemm(a, b, out16, aux=aux, act=2, colsum=cs)
+    assert rel_err(out16, out) < 4e-3
+    assert rel_err(cs, 1 + out.sum(0)) < 1e-4
     # q-scale on the first 256 columns
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
     ops.gemm(a, b, out, bias=bias, col_scale=0.125, col_scale_ncols=256)
@@ -130,8 +136,10 @@ def test_layernorm_fwd_bwd(ops, rows, D):
     a1h, a2h = a1.to(torch.bfloat16), a2.to(torch.bfloat16)
     ops.layernorm_bwd(dy16, x, g, mean, rstd, add1=a1h, add2=a2h, dx=dx, dx16=dx16)
     assert rel_err(dx, xr2.grad + a1h.float() + a2h.float()) < 1e-5
-    ops.layernorm_bwd(dy16, x, g, mean, rstd, add1=a1, add2=a2h, dx16=dx16)          # mixed dtypes, bf16-only output
+    cs = torch.ones(D, device="cuda")
+    ops.layernorm_bwd(dy16, x, g, mean, rstd, add1=a1, add2=a2h, dx16=dx16, colsum_dx=cs)   # mixed dtypes, bf16-only output
     assert rel_err(dx16, xr2.grad + a1 + a2h.float()) < 4e-3
+    assert rel_err(cs, 1 + (xr2.grad + a1 + a2h.float()).sum(0)) < 1e-4
 
 
 def test_layernorm_fused_add(ops):
