@@ -13,6 +13,8 @@
 // One CTA per SM, 128 x BLOCK_N output tile, 64-deep k-blocks, 4-6 stage TMA->smem ring, fp32 accumulators
 // double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..11 = epilogue.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "egovlp_b200.h"
 
@@ -44,10 +46,15 @@ struct EpiParams {
   float* colsum;    // optional fp32 [N]: accumulates the column sums of the stored values (bias gradient)
 };
 
-template <int BLOCK_N>
+// TWO = CTA pair (cta_group::2): a 256 x 256 tile per cluster, each CTA stages its 128 rows of A and HALF of B
+// (128 of the 256 n-rows).  Every smem byte then feeds twice the MMA work, which is what the 128 B/clk shared
+// memory port needs: in single-CTA mode TMA writes (96 B/clk) + UMMA operand reads (96 B/clk) oversubscribe it.
+template <int BLOCK_N, bool TWO>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int B_ROWS = TWO ? BLOCK_N / 2 : BLOCK_N;
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGES = (BLOCK_N == 256 && !TWO) ? 4 : 6;
+  static constexpr int TILE_M = TWO ? 2 * BLOCK_M : BLOCK_M;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
   static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;
   static constexpr int SMEM_BYTES =
@@ -100,11 +107,14 @@ __device__ __forceinline__ void store_bf16_coalesced(const uint8_t* stg_gen, int
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                          int K, int num_m_blocks, int num_n_blocks, int kb_per_split, int num_splits, EpiParams ep) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, TWO>;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0u;       // CTA of the pair; rank 0 issues the MMAs
+  const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int STAGES = C::STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -138,13 +148,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS);
+      mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS * (TWO ? 2 : 1));   // pair: both CTAs' epilogues report to rank 0
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (TWO) tmem_alloc_2cta(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -153,40 +167,45 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      for (int unit = worker; unit < num_units; unit += num_workers) {
         const int split = unit / num_tiles, tile = unit - split * num_tiles;
         const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
         const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+        const int m_row = m_blk * C::TILE_M + (int)rank * BLOCK_M;          // this CTA's 128 rows of A
+        const int n_row = n_blk * BLOCK_N + (int)rank * C::B_ROWS;           // this CTA's rows of B (all, or its half)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, A_STAGE_BYTES + C::B_STAGE_BYTES);
+          // pair: rank 0 expects the bytes of BOTH CTAs; every load credits rank 0's barrier
+          if (!TWO || rank == 0) mbar_expect_tx(fb, (A_STAGE_BYTES + C::B_STAGE_BYTES) * (TWO ? 2 : 1));
           const uint32_t a_dst = sA + stage * A_STAGE_BYTES, b_dst = sB + stage * C::B_STAGE_BYTES;
+          auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+            if (TWO) tma_load_2d_2sm(dst, tm, fb, c0, c1);
+            else tma_load_2d(dst, tm, fb, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(a_dst, &tmA, fb, kb * BLOCK_K, m_blk * BLOCK_M);
+            load(a_dst, &tmA, kb * BLOCK_K, m_row);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i)
-              tma_load_2d(a_dst + i * MN_ATOM_BYTES, &tmA, fb, m_blk * BLOCK_M + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < BLOCK_M / 64; ++i) load(a_dst + i * MN_ATOM_BYTES, &tmA, m_row + i * 64, kb * BLOCK_K);
           }
           if (!B_MN) {
-            tma_load_2d(b_dst, &tmB, fb, kb * BLOCK_K, n_blk * BLOCK_N);
+            load(b_dst, &tmB, kb * BLOCK_K, n_row);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i)
-              tma_load_2d(b_dst + i * MN_ATOM_BYTES, &tmB, fb, n_blk * BLOCK_N + i * 64, kb * BLOCK_K);
+            for (int i = 0; i < C::B_ROWS / 64; ++i) load(b_dst + i * MN_ATOM_BYTES, &tmB, n_row + i * 64, kb * BLOCK_K);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (rank 0 of a pair issues for both SMs) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(C::TILE_M, BLOCK_N, A_MN, B_MN);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+    for (int unit = worker; unit < num_units; unit += num_workers, ++it) {
       const int split = unit / num_tiles;
       const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
       const int acc = it & 1;
@@ -205,10 +224,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                                         : make_smem_desc_sw128(a_src + k * (UMMA_K * 2), 16, 1024);
             const uint64_t bdesc = B_MN ? make_smem_desc_sw128(b_src + k * (UMMA_K * 128), MN_ATOM_BYTES, 1024)
                                         : make_smem_desc_sw128(b_src + k * (UMMA_K * 2), 16, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (TWO) umma_bf16_ss_2cta(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + 8 * stage);
-          if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * acc);
+          if (TWO) {
+            umma_commit_2cta(empty_bar + 8 * stage);                 // frees the stage in both CTAs
+            if (kb == kb1 - 1) umma_commit_2cta(tfull_bar + 8 * acc);
+          } else {
+            umma_commit(empty_bar + 8 * stage);
+            if (kb == kb1 - 1) umma_commit(tfull_bar + 8 * acc);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -223,14 +248,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const uint32_t stg = epi_stage + e * 4096;
     const uint8_t* stg_gen = smem_gen + (stg - smem_base);
     int it = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++it) {
+    for (int unit = worker; unit < num_units; unit += num_workers, ++it) {
       const int split = unit / num_tiles, tile = unit - split * num_tiles;
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row0 = m_blk * BLOCK_M + q * 32;     // first of this warp's 32 rows
+      const int row0 = m_blk * C::TILE_M + (int)rank * BLOCK_M + q * 32;     // first of this warp's 32 rows
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
       // Each chunk: TMEM -> registers in row-owner layout (lane = row, 32 consecutive columns) -> per-column math
       // -> warp-private swizzled smem transpose -> coalesced layout (a row's 64/128 B handled by 4/8 adjacent lanes)
@@ -244,7 +269,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+          if (lane == 0) {
+            if (TWO && rank != 0) mbar_arrive_remote(mapa_shared(tempty_bar + 8 * acc, 0));
+            else mbar_arrive(tempty_bar + 8 * acc);
+          }
         }
         const int n0 = n_blk * BLOCK_N + half * COLS_PER_WARP + c;
         if (n0 >= N) continue;     // warp-uniform
@@ -338,51 +366,71 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (TWO) cluster_sync_all();      // the peer may still be reading this CTA's smem / signalling its barriers
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (TWO) tmem_dealloc_2cta(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO>
 int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int splits,
            const EpiParams& ep, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, TWO>;
   CUtensorMap tmA, tmB;
   int rc;
   if (!A_MN) rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K);
   else       rc = make_tmap_2d_bf16(&tmA, A, K, M, lda, BLOCK_K, 64);
   if (rc) return rc;
-  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, BLOCK_N, BLOCK_K);
+  if (!B_MN) rc = make_tmap_2d_bf16(&tmB, B, N, K, ldb, C::B_ROWS, BLOCK_K);
   else       rc = make_tmap_2d_bf16(&tmB, B, K, N, ldb, BLOCK_K, 64);
   if (rc) return rc;
-  const int num_m_blocks = (M + BLOCK_M - 1) / BLOCK_M, num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
+  const int num_m_blocks = (M + C::TILE_M - 1) / C::TILE_M, num_n_blocks = (N + BLOCK_N - 1) / BLOCK_N;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   splits = max(1, min(splits, num_kb));
   const int kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty splits
   const int units = num_m_blocks * num_n_blocks * splits;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN, TWO>;
   static bool attr_set = false;
   if (!attr_set) {
     EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int grid = min(units, num_sms());
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, M, N, K, num_m_blocks, num_n_blocks, kb_per_split,
-                                                     splits, ep);
-  EGOVLP_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  const int workers = min(units, TWO ? num_sms() / 2 : num_sms());
+  cfg.gridDim = dim3(TWO ? 2 * workers : workers);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  if (TWO) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  EGOVLP_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, M, N, K, num_m_blocks, num_n_blocks, kb_per_split, splits, ep));
   return EGOVLP_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool TWO>
 int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void* B, long long ldb, int M, int N, int K,
                    int splits, const EpiParams& ep, cudaStream_t stream) {
-  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  if (!a_mn && b_mn) return launch<BLOCK_N, false, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  if (a_mn && b_mn) return launch<BLOCK_N, true, true>(A, lda, B, ldb, M, N, K, splits, ep, stream);
-  return launch<BLOCK_N, true, false>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && !b_mn) return launch<BLOCK_N, false, false, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (!a_mn && b_mn) return launch<BLOCK_N, false, true, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  if (a_mn && b_mn) return launch<BLOCK_N, true, true, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+  return launch<BLOCK_N, true, false, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
+
+// EGOVLP_GEMM_1CTA=1 keeps every shape on the single-CTA kernels (tests exercise both)
+inline bool force_one_cta() {
+  const char* e = getenv("EGOVLP_GEMM_1CTA");
+  return e && e[0] == '1';
 }
 
 }  // namespace
@@ -412,6 +460,8 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols; ep.res_row_mod = e->res_row_mod;
   ep.colsum = e->colsum;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N % 256 == 0) return dispatch_major<256>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
-  return dispatch_major<128>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+  if (N % 256 == 0 && !force_one_cta())     // CTA-pair 256 x 256 tiles
+    return dispatch_major<256, true>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+  if (N % 256 == 0) return dispatch_major<256, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+  return dispatch_major<128, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
 }

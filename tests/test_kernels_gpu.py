@@ -12,6 +12,13 @@ def ops():
     return ops
 
 
+@pytest.fixture(params=["pair", "single"])
+def gemm_mode(request, monkeypatch):
+    """Run every GEMM test on both tile schedulers: CTA-pair 256x256 (default for N % 256 == 0) and single-CTA."""
+    monkeypatch.setenv("EGOVLP_GEMM_1CTA", "1" if request.param == "single" else "0")
+    return request.param
+
+
 def rel_err(a, b):
     return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-30)).item()
 
@@ -23,7 +30,7 @@ def mk(shape, seed, scale=1.0, dtype=torch.bfloat16):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 768), (300, 768, 768), (1570, 2304, 768),
                                    (130, 128, 64), (200, 64, 128), (1000, 3072, 768), (257, 768, 3072), (64, 32, 64)])
-def test_gemm_kmajor_bias(ops, M, N, K):
+def test_gemm_kmajor_bias(ops, M, N, K, gemm_mode):
     a, b = mk((M, K), 1), mk((N, K), 2, 0.05)
     bias = mk((N,), 3, dtype=torch.float32)
     out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
@@ -36,7 +43,7 @@ def test_gemm_kmajor_bias(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 128), (300, 768, 2304), (1000, 3072, 768), (200, 64, 128)])
-def test_gemm_b_mn_major_dgrad(ops, M, N, K):
+def test_gemm_b_mn_major_dgrad(ops, M, N, K, gemm_mode):
     """dx = dy @ W with W stored [K, N] (n contiguous): the dgrad form."""
     a, w = mk((M, K), 4), mk((K, N), 5, 0.05)
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
@@ -46,7 +53,7 @@ def test_gemm_b_mn_major_dgrad(ops, M, N, K):
 
 @pytest.mark.parametrize("Mtok,N,Kin,split", [(512, 256, 256, 1), (1000, 768, 768, 4), (3137, 2304, 768, 7),
                                               (777, 128, 64, 3)])
-def test_gemm_both_mn_major_wgrad(ops, Mtok, N, Kin, split):
+def test_gemm_both_mn_major_wgrad(ops, Mtok, N, Kin, split, gemm_mode):
     """dW[N,Kin] += dy^T x : contraction over tokens, both operands token-major; split-K atomics."""
     mt = (Mtok + 7) // 8 * 8
     dy, x = mk((mt, N), 6), mk((mt, Kin), 7)
@@ -58,7 +65,7 @@ def test_gemm_both_mn_major_wgrad(ops, Mtok, N, Kin, split):
     assert rel_err(out, ref) < 2e-5
 
 
-def test_gemm_epilogues(ops):
+def test_gemm_epilogues(ops, gemm_mode):
     M, N, K = 515, 768, 256
     a, b = mk((M, K), 9), mk((N, K), 10, 0.06)
     bias = mk((N,), 11, dtype=torch.float32)
@@ -94,7 +101,7 @@ def test_gemm_epilogues(ops):
     assert rel_err(out, ref) < 2e-5
 
 
-def test_gemm_strided_views(ops):
+def test_gemm_strided_views(ops, gemm_mode):
     """Operands / outputs that are column slices of wider buffers (ld > width)."""
     M, N, K = 384, 256, 192
     abuf, bbuf = mk((M, 3 * K), 14), mk((N, 2 * K), 15, 0.05)
