@@ -44,6 +44,7 @@ struct EpiParams {
   int col_scale_ncols;
   int res_row_mod;  // 0: residual row = m; else residual row = m % res_row_mod (broadcast table)
   float* colsum;    // optional fp32 [N]: accumulates the column sums of the stored values (bias gradient)
+  int debug_no_loads;  // profiling aid (EGOVLP_GEMM_DEBUG_NOLOADS=1): skip the TMA loads, MMAs run on stale smem
 };
 
 // TWO = CTA pair (cta_group::2): a 256 x 256 tile per cluster, each CTA stages its 128 rows of A and HALF of B
@@ -177,6 +178,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
           // pair: rank 0 expects the bytes of BOTH CTAs; every load credits rank 0's barrier
+          if (ep.debug_no_loads) {
+            if (!TWO || rank == 0) mbar_arrive(fb);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!TWO || rank == 0) mbar_expect_tx(fb, (A_STAGE_BYTES + C::B_STAGE_BYTES) * (TWO ? 2 : 1));
           const uint32_t a_dst = sA + stage * A_STAGE_BYTES, b_dst = sB + stage * C::B_STAGE_BYTES;
           auto load = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
@@ -459,8 +465,14 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   ep.out_mode = e->out_mode; ep.act = e->act; ep.alpha = e->alpha;
   ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols; ep.res_row_mod = e->res_row_mod;
   ep.colsum = e->colsum;
+  {
+    const char* dbg = getenv("EGOVLP_GEMM_DEBUG_NOLOADS");
+    ep.debug_no_loads = (dbg && dbg[0] == '1') ? 1 : 0;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (N % 256 == 0 && !force_one_cta())     // CTA-pair 256 x 256 tiles
+  // CTA-pair 256 x 256 tiles for the K-major-A shapes (fwd, dgrad); the token-contraction wgrad (both operands
+  // MN-major, split-K) measured 3-8 % faster on single-CTA 128 x 256 tiles (tools/bench_gemm_modes.py)
+  if (N % 256 == 0 && !force_one_cta() && !(a_mn_major && b_mn_major))
     return dispatch_major<256, true>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
   if (N % 256 == 0) return dispatch_major<256, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
   return dispatch_major<128, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
