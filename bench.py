@@ -259,15 +259,34 @@ def main():
 
     e2e = None
     if not args.no_e2e:
-        def e2e_step():
-            l = step(to_device())
-            return l.item()                                   # D2H read of the loss every step
-        for _ in range(1):
-            e2e_step()
-        ms_e2e, _ = timed(args.steps, e2e_step)
+        from egovlp_b200.data import DevicePrefetcher
+
+        def host_batches(n, video):
+            for _ in range(n):
+                yield {"video": video, "text": {"input_ids": host["ids"], "attention_mask": host["mask"]},
+                       "verb_vec": host["verb"], "noun_vec": host["noun"]}
+
+        def run_e2e(video):
+            n = args.steps + 1
+            it = iter(DevicePrefetcher(host_batches(n, video), dev))     # every batch: pinned host -> device copy
+            step(next(it)).item()                                        # untimed first step
+            def one():
+                return step(next(it)).item()                             # D2H read of the loss every step
+            ms, _ = timed(args.steps, one)
+            return ms
+
+        ms_e2e = run_e2e(host["video"])
         e2e = {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": h2d_bytes,
                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
-               "note": "per step: pinned-host fp32 video/ids/mask/tags -> device, model(data) public API, loss.item()"}
+               "note": "per step: pinned-host fp32 video/ids/mask/tags -> device (one batch in flight on a copy "
+                       "stream, egovlp_b200.data.DevicePrefetcher), model(data) public API, loss.item()"}
+        # same step fed with uint8 frames (normalisation fused into the patch-embedding kernel): 4x fewer H2D bytes
+        mean = torch.tensor(syn.IMAGENET_MEAN).view(1, 1, 3, 1, 1)
+        std = torch.tensor(syn.IMAGENET_STD).view(1, 1, 3, 1, 1)
+        video_u8 = ((host["video"] * std + mean).clamp(0, 1) * 255).round().to(torch.uint8).pin_memory()
+        ms_u8 = run_e2e(video_u8)
+        e2e["uint8_frames"] = {"value": B * world * args.steps / (ms_u8 / 1e3), "ms_per_step": ms_u8 / args.steps,
+                               "h2d_bytes_per_step": h2d_bytes - host["video"].numel() * 3}
 
     if rank == 0:
         peaks, peak_src = measured_peaks()

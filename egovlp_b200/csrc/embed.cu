@@ -38,6 +38,36 @@ __global__ void im2col_kernel(const float* __restrict__ video, bf16* __restrict_
   }
 }
 
+// Same from uint8 frames with the dataset normalisation fused: v = (p / 255 - mean[c]) / std[c]
+// (data_loader/transforms.py:38-41 applied on the GPU; H2D traffic drops 4x -- SURVEY.md section 8f row 2).
+__global__ void im2col_u8_kernel(const uint8_t* __restrict__ video, bf16* __restrict__ patches, int B, int T, int C,
+                                 int H, int W, int P, int S, float3 mean, float3 inv_std) {
+  const int gw = W / P, gh = H / P, N = gw * gh, K = C * P * P, P4 = P / 4;
+  const long long total = (long long)B * T * N * C * P * P4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int x4 = r % P4; r /= P4;
+    const int iy = r % P; r /= P;
+    const int c = r % C; r /= C;
+    const int n = r % N; r /= N;
+    const int t = r % T;
+    const int b = r / T;
+    const int py = n / gw, px = n % gw;
+    const uchar4 v = *reinterpret_cast<const uchar4*>(
+        video + ((((long long)b * T + t) * C + c) * H + (py * P + iy)) * W + px * P + x4 * 4);
+    const float m = c == 0 ? mean.x : c == 1 ? mean.y : mean.z, is = c == 0 ? inv_std.x : c == 1 ? inv_std.y : inv_std.z;
+    const float k = 1.f / 255.f;
+    bf16* dst = patches + ((long long)b * S + 1 + t * N + n) * K + c * P * P + iy * P + x4 * 4;
+    *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16x2((v.x * k - m) * is, (v.y * k - m) * is),
+                                                pack_bf16x2((v.z * k - m) * is, (v.w * k - m) * is));
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)B * K / 2;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = i / (K / 2), k2 = i % (K / 2);
+    reinterpret_cast<uint32_t*>(patches + (long long)b * S * K)[k2] = 0u;
+  }
+}
+
 __global__ void pos_table_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                  const float* __restrict__ temporal, const float* __restrict__ bias,
                                  float* __restrict__ R, int T, int N, int D) {
@@ -103,6 +133,21 @@ extern "C" int egovlp_patch_im2col(const float* video, void* patches_bf16, int B
   const long long blocks = (total + 255) / 256;
   const int grid = (int)(blocks > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : blocks);
   im2col_kernel<<<grid, 256, 0, ST(stream)>>>(video, reinterpret_cast<bf16*>(patches_bf16), B, T, C, H, W, P, S);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+extern "C" int egovlp_patch_im2col_u8(const uint8_t* video, void* patches_bf16, int B, int T, int C, int H, int W, int P,
+                                      const float* host_mean3, const float* host_std3, void* stream) {
+  EGOVLP_CHECK_ARG(video && patches_bf16 && host_mean3 && host_std3 && B > 0 && T > 0 && C == 3, "patch_im2col_u8: bad args");
+  EGOVLP_CHECK_ARG(P % 4 == 0 && H % P == 0 && W % P == 0 && W % 4 == 0, "patch_im2col_u8: H=%d W=%d P=%d unsupported", H, W, P);
+  const int S = 1 + T * (H / P) * (W / P);
+  const long long total = (long long)B * T * (H / P) * (W / P) * C * P * (P / 4);
+  const long long blocks = (total + 255) / 256;
+  const int grid = (int)(blocks > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : blocks);
+  const float3 mean = make_float3(host_mean3[0], host_mean3[1], host_mean3[2]);
+  const float3 inv = make_float3(1.f / host_std3[0], 1.f / host_std3[1], 1.f / host_std3[2]);
+  im2col_u8_kernel<<<grid, 256, 0, ST(stream)>>>(video, reinterpret_cast<bf16*>(patches_bf16), B, T, C, H, W, P, S, mean, inv);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }

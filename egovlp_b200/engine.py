@@ -93,19 +93,23 @@ class PatchEmbedFn(torch.autograd.Function):
     """VideoPatchEmbed + cls/pos/temporal embedding assembly (model/video_transformer.py:72-77, 304-321)."""
 
     @staticmethod
-    def forward(ctx, video, cls_token, pos_embed, temporal_embed, w, b, cache):
+    def forward(ctx, video, cls_token, pos_embed, temporal_embed, w, b, cache, norm=None):
         B, T, C, H, W = video.shape
         D, _, P, _ = w.shape
         N = (H // P) * (W // P)
         S = 1 + T * N
         K = C * P * P
-        video = video.contiguous().float()
-        patches = _empty((B * S, K), BF16, video)
-        ops.patch_im2col(video, patches, P)
-        table = _empty((S, D), F32, video)
+        patches = _empty((B * S, K), BF16, w)
+        if video.dtype == torch.uint8:          # raw frames: dataset normalisation fused into the unfold
+            mean, std = norm if norm is not None else ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))
+            ops.patch_im2col_u8(video.contiguous(), patches, P, mean, std)
+        else:
+            video = video.contiguous().float()
+            ops.patch_im2col(video, patches, P)
+        table = _empty((S, D), F32, w)
         ops.video_pos_table(cls_token.detach().contiguous(), pos_embed.detach().contiguous(),
                             temporal_embed.detach().contiguous(), b.detach(), table, T, N, D)
-        x = _empty((B * S, D), F32, video)
+        x = _empty((B * S, D), F32, w)
         ops.gemm(patches, cache.get(w, (D, K)), x, bias=b.detach(), residual=table, res_row_mod=S)
         ctx.dims = (B, T, N, D, K, temporal_embed.shape[1])
         ctx.save_for_backward(patches)
@@ -123,7 +127,7 @@ class PatchEmbedFn(torch.autograd.Function):
         tmp = _empty(((1 + T * N) * D,), F32, dx)
         ops.video_embed_bwd(dx, tmp, dcls, dpos, dtemp, dbias, B, T, N, D)
         P = int(round((K // 3) ** 0.5))
-        return None, dcls, dpos, dtemp, dw.view(D, 3, P, P), dbias, None
+        return None, dcls, dpos, dtemp, dw.view(D, 3, P, P), dbias, None, None
 
 
 class SpaceTimeBlockFn(torch.autograd.Function):

@@ -173,8 +173,10 @@ class SpaceTimeTransformer(nn.Module):
         assert F <= self.num_frames
         cache = self._bf16_cache
         pe = self.patch_embed
+        # uint8 frames are normalised on the fly with `input_norm` = (mean, std) (default: ImageNet, as the reference's
+        # data_loader/transforms.py); float frames are taken as already normalised (the reference contract).
         x = engine.PatchEmbedFn.apply(x, self.cls_token, self.pos_embed, self.temporal_embed, pe.proj.weight,
-                                      pe.proj.bias, cache)
+                                      pe.proj.bias, cache, getattr(self, "input_norm", None))
         n = (H // pe.patch_size[0]) * (W // pe.patch_size[1])
         for blk in self.blocks:
             x = blk(x, time_n=n, space_f=F, cache=cache)

@@ -165,6 +165,13 @@ def patch_im2col(video, patches, P):
     call("egovlp_patch_im2col", _ptr(video), _ptr(patches), B, T, Cc, H, W, P, _stream())
 
 
+def patch_im2col_u8(video, patches, P, mean, std):
+    assert video.is_cuda and video.dtype == torch.uint8 and video.is_contiguous()
+    B, T, Cc, H, W = video.shape
+    m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+    call("egovlp_patch_im2col_u8", _ptr(video), _ptr(patches), B, T, Cc, H, W, P, m3, s3, _stream())
+
+
 def video_pos_table(cls_token, pos_embed, temporal_embed, conv_bias, table, T, N, D):
     call("egovlp_video_pos_table", _ptr(cls_token), _ptr(pos_embed), _ptr(temporal_embed), _ptr(conv_bias),
          _ptr(table), T, N, D, _stream())

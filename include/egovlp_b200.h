@@ -113,6 +113,10 @@ int egovlp_divided_attn_bwd(const void* qkv, const void* out, const void* dout, 
  *     and the conv bias gradient dbias[D]; tmp_SD is an fp32 workspace of S*D floats.
  */
 int egovlp_patch_im2col(const float* video, void* patches_bf16, int B, int T, int C, int H, int W, int P, void* stream);
+/* uint8 frames [B,T,3,H,W] with the dataset normalisation (data_loader/transforms.py:38-41) fused:
+ * v = (p/255 - mean[c]) / std[c]; host_mean3 / host_std3 are HOST arrays of 3 floats. */
+int egovlp_patch_im2col_u8(const uint8_t* video, void* patches_bf16, int B, int T, int C, int H, int W, int P,
+                           const float* host_mean3, const float* host_std3, void* stream);
 int egovlp_video_pos_table(const float* cls_token, const float* pos_embed, const float* temporal_embed,
                            const float* conv_bias, float* table, int T, int N, int D, void* stream);
 int egovlp_video_embed_bwd(const float* dx, float* tmp_SD, float* dcls, float* dpos, float* dtemporal, float* dbias,

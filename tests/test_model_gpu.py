@@ -248,3 +248,32 @@ def test_training_steps_reduce_loss_tiny():
         opt.step()
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0] - 0.05, losses
+
+
+def test_uint8_frames_match_normalised_float_frames():
+    """uint8 frames + fused ImageNet normalisation == float frames normalised on the host."""
+    from egovlp_b200 import synthetic as syn
+    from egovlp_b200.model.video_transformer import SpaceTimeTransformer
+    sd = syn.seeded_state_dict(syn.TINY_DIMS, seed=5, text=False, proj=False)
+    net = SpaceTimeTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, num_frames=4,
+                               time_init="zeros", num_classes=0)
+    net.load_state_dict({k[len("video_model."):]: v for k, v in sd.items()})
+    net.cuda()
+    g = torch.Generator().manual_seed(8)
+    u8 = torch.randint(0, 256, (3, 4, 3, 32, 32), generator=g, dtype=torch.uint8)
+    mean = torch.tensor(syn.IMAGENET_MEAN).view(1, 1, 3, 1, 1)
+    std = torch.tensor(syn.IMAGENET_STD).view(1, 1, 3, 1, 1)
+    flt = (u8.float() / 255 - mean) / std
+    with torch.no_grad():
+        a, b = net(u8.cuda()), net(flt.cuda())
+    assert rel(a, b) < 2e-3
+
+
+def test_device_prefetcher_preserves_batches():
+    from egovlp_b200.data import DevicePrefetcher
+    batches = [{"video": torch.full((2, 3), float(i)).pin_memory(), "text": {"ids": torch.arange(4).pin_memory() + i}}
+               for i in range(5)]
+    out = list(DevicePrefetcher(batches, "cuda"))
+    assert len(out) == 5
+    for i, o in enumerate(out):
+        assert o["video"].is_cuda and torch.all(o["video"] == i) and torch.equal(o["text"]["ids"].cpu(), torch.arange(4) + i)
