@@ -9,79 +9,61 @@ namespace {
 
 constexpr int LN_WARPS = 8;
 
-// Forward.  Persistent: each warp walks rows with a grid stride and keeps the NEXT row's loads in flight while it
-// reduces / normalises / stores the current one (a streaming kernel is only as fast as its bytes in flight).
+// Forward: one row per warp, 8 rows per CTA (a persistent, register-prefetching variant measured slower: 36 % vs
+// 55 % of the HBM copy bandwidth at M = 50k rows -- occupancy beats explicit prefetch here).
 template <int NV>  // NV float4 per lane: covers D <= NV*128
-__global__ void __launch_bounds__(LN_WARPS * 32, 2)
+__global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ add,
                      float* __restrict__ sum_out, const float* __restrict__ gamma, const float* __restrict__ beta,
                      bf16* __restrict__ y16, float* __restrict__ y32, float* __restrict__ mean_out,
                      float* __restrict__ rstd_out, int rows, int D, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int stride = gridDim.x * LN_WARPS;
-  int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= rows) return;
-  auto load_row = [&](int r, float4 (&v)[NV]) {
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + (long long)row * ldx;
+  float4 v[NV];
+  float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        v[i] = *reinterpret_cast<const float4*>(x + (long long)r * ldx + c);
-        if (add) {
-          const float4 a = *reinterpret_cast<const float4*>(add + (long long)r * D + c);
-          v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
-        }
-      } else {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      v[i] = *reinterpret_cast<const float4*>(xr + c);
+      if (add) {
+        const float4 a = *reinterpret_cast<const float4*>(add + (long long)row * D + c);
+        v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
       }
+      if (sum_out) *reinterpret_cast<float4*>(sum_out + (long long)row * D + c) = v[i];
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  };
-  float4 v[NV], nv[NV];
-  load_row(row, v);
-  while (true) {
-    const int nrow = row + stride;
-    const bool has_next = nrow < rows;
-    if (has_next) load_row(nrow, nv);
-    float s = 0.f;
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        if (sum_out) *reinterpret_cast<float4*>(sum_out + (long long)row * D + c) = v[i];
-        s += v[i].x + v[i].y + v[i].z + v[i].w;
-      }
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + cc * cc + d * d;
     }
-    const float mean = warp_sum(s) / D;
-    float q = 0.f;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-        q += a * a + b * b + cc * cc + d * d;
-      }
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < D) {
+      const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+      const float4 b = *reinterpret_cast<const float4*>(beta + c);
+      const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (y16) *reinterpret_cast<uint2*>(y16 + (long long)row * D + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      if (y32) *reinterpret_cast<float4*>(y32 + (long long)row * D + c) = make_float4(o0, o1, o2, o3);
     }
-    const float rstd = rsqrtf(warp_sum(q) / D + eps);
-    if (lane == 0) {
-      if (mean_out) mean_out[row] = mean;
-      if (rstd_out) rstd_out[row] = rstd;
-    }
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (i * 32 + lane) * 4;
-      if (c < D) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-        const float o0 = (v[i].x - mean) * rstd * g.x + b.x, o1 = (v[i].y - mean) * rstd * g.y + b.y;
-        const float o2 = (v[i].z - mean) * rstd * g.z + b.z, o3 = (v[i].w - mean) * rstd * g.w + b.w;
-        if (y16) *reinterpret_cast<uint2*>(y16 + (long long)row * D + c) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
-        if (y32) *reinterpret_cast<float4*>(y32 + (long long)row * D + c) = make_float4(o0, o1, o2, o3);
-      }
-    }
-    if (!has_next) break;
-    row = nrow;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = nv[i];
   }
 }
 
@@ -241,7 +223,7 @@ template <int NV>
 int launch_ln_fwd(const float* x, long long ldx, const float* add, float* sum_out, const float* gamma,
                   const float* beta, void* y16, float* y32, float* mean, float* rstd, int rows, int D, float eps,
                   cudaStream_t st) {
-  const int grid = min((rows + LN_WARPS - 1) / LN_WARPS, num_sms() * 2);
+  const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   layernorm_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, st>>>(x, ldx, add, sum_out, gamma, beta,
                                                           reinterpret_cast<bf16*>(y16), y32, mean, rstd, rows, D, eps);
   EGOVLP_CHECK_LAUNCH();
