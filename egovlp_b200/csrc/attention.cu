@@ -20,6 +20,12 @@
 #include "egovlp_b200.h"
 
 namespace egovlp {
+
+// tcgen05 / TMEM space-attention forward (attention_tc.cu)
+bool space_attn_tc_supported(int N);
+int space_attn_fwd_tc(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N, int H,
+                      cudaStream_t st);
+
 namespace {
 
 constexpr int HD = 64;            // head dim
@@ -1126,7 +1132,10 @@ extern "C" int egovlp_divided_attn_fwd(const void* qkv, void* out, float* lse, f
     KERN<<<grid, W * 32, smem, st>>>(tm, q, o, lse, cls_part, G, ##__VA_ARGS__);                              \
   } while (0)
   const bool generic = force_generic() || (mode == 0 && !time_fast_ok(G));
-  if (generic) {
+  if (!generic && mode == 1 && space_attn_tc_supported(N)) {     // tcgen05 / TMEM kernel
+    rc = space_attn_fwd_tc(qkv, out, lse, cls_part, B, T, N, H, st);
+    if (rc) return rc;
+  } else if (generic) {
     if (G.NPAD > 128) LAUNCH_FWD((divided_attn_fwd_kernel<7, 2>), 7);
     else LAUNCH_FWD((divided_attn_fwd_kernel<4, 3>), 4);
   } else if (mode == 1) {     // space: 13 row tiles over 7 warps, 2 CTAs / SM at 196 patches

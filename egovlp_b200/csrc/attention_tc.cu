@@ -1,0 +1,301 @@
+// Space attention forward on tcgen05 / TMEM (the N-length attention of VarAttention, model/video_transformer.py:
+// 109-133 in '(b f) n d' mode): S = Q K^T and O = P V are UMMA tiles, Q/K/V arrive by TMA, the softmax runs on
+// the TMEM accumulator rows.  Same inputs / outputs / CLS semantics as the mma.sync kernels in attention.cu.
+//
+// One persistent CTA per SM loops over the (b, head, frame) groups with double-buffered Q/K/V tiles:
+//   warp 0   TMA producer: per group 3 boxes of N patch rows + 3 one-row boxes for the CLS q/k/v (row N of each tile)
+//   warp 1   MMA issuer:   S_t[128 x NKP] = Q_t K^T for the two 128-row query tiles (4 UMMAs each, K = 64), then, as
+//            soon as the softmax warps have written P_t (bf16, 128B-swizzled K-major tile in smem),
+//            O[128 x 64] = P_t V (NKP/16 UMMAs, V read as an MN-major B operand straight from the [key, d] tile)
+//   warp 2   TMEM allocator (512 columns: S_0 | S_1 | O)
+//   warps 4-7 one thread per query row: two passes over the S row in TMEM (max; exp2 / sum / bf16 P), then the
+//            O row: normalise, store 128 contiguous bytes; the CLS query row leaves its (max, sum, acc) partial.
+// Rows >= N+1 of a tile are padding: their results are never stored (UMMA rows are independent).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "egovlp_b200.h"
+
+namespace egovlp {
+namespace {
+
+constexpr int HD = 64;
+constexpr int ROWB = 128;                 // bytes per head-row
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int TILE_ROWS = 208;            // rows reserved per Q/K/V tile (NKP <= 208 -> 26 KB, 1024-aligned)
+constexpr int TILE_BYTES = TILE_ROWS * ROWB;
+constexpr int P_BLOCK_BYTES = 128 * ROWB; // one 64-key column block of P for 128 rows
+constexpr int P_BYTES = 4 * P_BLOCK_BYTES;
+constexpr int TC_THREADS = 256;
+constexpr int S1_COL = 224, O_COL = 448;  // TMEM columns: S_0 at 0, S_1 at 224, O at 448 (NKP <= 224)
+
+struct TcGeom {
+  int B, H, T, N, S, D, NK, NKP, groups;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_cls,
+                         bf16* __restrict__ out, float* __restrict__ lse_out, float* __restrict__ cls_part, TcGeom G) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // [buf0: Q K V][buf1: Q K V][P][barriers]
+  const uint32_t sP = base + 6 * TILE_BYTES;
+  const uint32_t bars = sP + P_BYTES;
+  const uint32_t full_bar = bars;            // 2
+  const uint32_t empty_bar = bars + 16;      // 2
+  const uint32_t sfull_bar = bars + 32;      // 2 (per query tile)
+  const uint32_t sfree_bar = bars + 48;      // 2
+  const uint32_t pready_bar = bars + 64;
+  const uint32_t pfree_bar = bars + 72;
+  const uint32_t ofull_bar = bars + 80;
+  const uint32_t ofree_bar = bars + 88;
+  const uint32_t tmem_slot = bars + 96;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NT = (G.NK + 127) / 128;          // query tiles (1 or 2)
+
+  // zero the padding rows NK .. TILE_ROWS-1 of every tile once (TMA never writes them): V pad rows must be finite
+  for (int i = threadIdx.x; i < 6 * (TILE_ROWS - G.NK) * 8; i += TC_THREADS) {
+    const int c = i & 7, rr = (i >> 3) % (TILE_ROWS - G.NK), tile = (i >> 3) / (TILE_ROWS - G.NK);
+    *reinterpret_cast<uint4*>(gen + tile * TILE_BYTES + (G.NK + rr) * ROWB + c * 16) = make_uint4(0, 0, 0, 0);
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_rows);
+    tma_prefetch_desc(&tm_cls);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+      mbar_init(sfull_bar + 8 * i, 1);
+      mbar_init(sfree_bar + 8 * i, 4);
+    }
+    mbar_init(pready_bar, 4);
+    mbar_init(pfree_bar, 1);
+    mbar_init(ofull_bar, 1);
+    mbar_init(ofree_bar, 4);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();       // the zero fill above must be visible to the UMMA (async proxy) reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int it = 0;
+      for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+        mbar_wait(empty_bar + 8 * buf, ((it >> 1) & 1) ^ 1);
+        const uint32_t fb = full_bar + 8 * buf;
+        mbar_expect_tx(fb, 3u * (uint32_t)G.NK * ROWB);
+        const uint32_t q = base + buf * 3 * TILE_BYTES;
+#pragma unroll
+        for (int w = 0; w < 3; ++w) {
+          tma_load_4d(q + w * TILE_BYTES, &tm_rows, fb, 0, 1 + f * G.N, w * G.H + h, b);
+          tma_load_4d(q + w * TILE_BYTES + G.N * ROWB, &tm_cls, fb, 0, 0, w * G.H + h, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =======================
+    const uint32_t idesc_s = make_idesc_bf16(128, G.NKP, false, false);
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, HD, false, true);     // B = V, MN-major (d contiguous)
+    int it = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t q = base + buf * 3 * TILE_BYTES, k = q + TILE_BYTES, v = k + TILE_BYTES;
+      mbar_wait(full_bar + 8 * buf, (it >> 1) & 1);
+      tc_fence_after();
+      for (int t = 0; t < NT; ++t) {
+        mbar_wait(sfree_bar + 8 * t, (it & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_smem_desc_sw128(q + t * 128 * ROWB + kk * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(k + kk * 32, 16, 1024);
+            umma_bf16_ss(tmem + (t ? S1_COL : 0), ad, bd, idesc_s, kk > 0);
+          }
+          umma_commit(sfull_bar + 8 * t);
+        }
+        __syncwarp();
+      }
+      for (int t = 0; t < NT; ++t) {
+        const int n = it * NT + t;
+        mbar_wait(pready_bar, n & 1);
+        mbar_wait(ofree_bar, (n & 1) ^ 1);
+        tc_fence_after();
+        if (lane == 0) {
+          for (int ks = 0; ks < G.NKP / 16; ++ks) {
+            const uint64_t ad = make_smem_desc_sw128(sP + (ks >> 2) * P_BLOCK_BYTES + (ks & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(v + ks * 16 * ROWB, 8192, 1024);
+            umma_bf16_ss(tmem + O_COL, ad, bd, idesc_o, ks > 0);
+          }
+          umma_commit(pfree_bar);
+          umma_commit(ofull_bar);
+          if (t == NT - 1) umma_commit(empty_bar + 8 * buf);     // every UMMA reading this Q/K/V buffer is done
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ======================= softmax + epilogue: one thread per query row =======================
+    const int qd = warp & 3;
+    const int r_in_tile = qd * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    int it = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++it) {
+      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+      for (int t = 0; t < NT; ++t) {
+        const int n = it * NT + t;
+        const int row = t * 128 + r_in_tile;             // query row of the group (N = CLS query)
+        const bool is_cls_q = row == G.N;
+        // the CLS key (column N) is visible to every patch query, and to the CLS query in the first frame only
+        const int ncols = (is_cls_q && f != 0) ? G.N : G.NK;
+        const uint32_t s_addr = tmem + lane_base + (t ? S1_COL : 0);
+        mbar_wait(sfull_bar + 8 * t, it & 1);
+        tc_fence_after();
+        // pass 1: row max
+        float mx = -INFINITY;
+        for (int c0 = 0; c0 < G.NKP; c0 += 32) {
+          uint32_t r[32];
+          if (c0 + 32 <= G.NKP) {
+            tmem_ld_32x32b_x32(s_addr + c0, r);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x32b_x16(s_addr + c0, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0xff800000u; }
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY);
+        }
+        const float ms = mx * LOG2E;
+        // pass 2: p = exp2(s*log2e - ms), row sum, bf16 P into the swizzled K-major smem tile
+        mbar_wait(pfree_bar, (n & 1) ^ 1);               // the previous P V product has consumed the P tile
+        float sum = 0.f;
+        for (int c0 = 0; c0 < G.NKP; c0 += 32) {
+          uint32_t r[32];
+          if (c0 + 32 <= G.NKP) {
+            tmem_ld_32x32b_x32(s_addr + c0, r);
+          } else {
+            uint32_t r16[16];
+            tmem_ld_32x32b_x16(s_addr + c0, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0xff800000u; }
+          }
+          tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            p[j] = (c0 + j < ncols) ? exp2f(__uint_as_float(r[j]) * LOG2E - ms) : 0.f;
+            sum += p[j];
+          }
+          const uint32_t blk = sP + (c0 >> 6) * P_BLOCK_BYTES + r_in_tile * ROWB;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c0 + 8 * c < G.NKP) {
+              const int chunk = ((c0 & 63) >> 3) + c;
+              const uint32_t a = blk + ((chunk ^ (r_in_tile & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(p[8 * c], p[8 * c + 1])),
+                           "r"(pack_bf16x2(p[8 * c + 2], p[8 * c + 3])), "r"(pack_bf16x2(p[8 * c + 4], p[8 * c + 5])),
+                           "r"(pack_bf16x2(p[8 * c + 6], p[8 * c + 7])));
+            }
+          }
+        }
+        // S_t fully read -> the MMA warp may overwrite it for the next group; P_t written -> P V may start
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(sfree_bar + 8 * t);
+          mbar_arrive(pready_bar);
+        }
+        // epilogue: O row
+        mbar_wait(ofull_bar, n & 1);
+        tc_fence_after();
+        uint32_t o[2][32];
+        tmem_ld_32x32b_x32(tmem + lane_base + O_COL, o[0]);
+        tmem_ld_32x32b_x32(tmem + lane_base + O_COL + 32, o[1]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ofree_bar);
+        if (row < G.N) {
+          const float inv = 1.f / sum;
+          const long long tok = (long long)b * G.S + 1 + f * G.N + row;
+          uint4* dst = reinterpret_cast<uint4*>(out + tok * G.D + h * HD);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t* s4 = &o[c >> 2][(c & 3) * 8];
+            dst[c] = make_uint4(pack_bf16x2(__uint_as_float(s4[0]) * inv, __uint_as_float(s4[1]) * inv),
+                                pack_bf16x2(__uint_as_float(s4[2]) * inv, __uint_as_float(s4[3]) * inv),
+                                pack_bf16x2(__uint_as_float(s4[4]) * inv, __uint_as_float(s4[5]) * inv),
+                                pack_bf16x2(__uint_as_float(s4[6]) * inv, __uint_as_float(s4[7]) * inv));
+          }
+          lse_out[((long long)(b * G.H + h)) * G.S + 1 + f * G.N + row] = mx + logf(sum);
+        } else if (is_cls_q) {
+          float* dst = cls_part + (((long long)(b * G.H + h)) * G.T + f) * 66;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) dst[j] = __uint_as_float(o[j >> 5][j & 31]);
+          dst[64] = mx;
+          dst[65] = sum;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+// geometry the tcgen05 kernel covers: two query tiles, keys padded to <= 208
+bool space_attn_tc_supported(int N) {
+  const char* e = getenv("EGOVLP_ATTN_TC");
+  if (e && e[0] == '0') return false;
+  const int NK = N + 1;
+  return NK > 128 && NK <= TILE_ROWS;
+}
+
+int space_attn_fwd_tc(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N, int H,
+                      cudaStream_t st) {
+  TcGeom G;
+  G.B = B; G.H = H; G.T = T; G.N = N; G.S = 1 + T * N; G.D = H * HD; G.NK = N + 1; G.NKP = (G.NK + 15) / 16 * 16;
+  G.groups = B * H * T;
+  const uint64_t W = 3ull * G.D;
+  const uint64_t dims[4] = {HD, (uint64_t)G.S, (uint64_t)(3 * H), (uint64_t)B};
+  const uint64_t strides[4] = {1, W, HD, (uint64_t)G.S * W};
+  const uint32_t box_rows[4] = {HD, (uint32_t)N, 1, 1};
+  const uint32_t box_cls[4] = {HD, 1, 1, 1};
+  CUtensorMap tm_rows, tm_cls;
+  int rc = make_tmap_nd_bf16(&tm_rows, qkv, 4, dims, strides, box_rows, true);
+  if (rc) return rc;
+  rc = make_tmap_nd_bf16(&tm_cls, qkv, 4, dims, strides, box_cls, true);
+  if (rc) return rc;
+  const int smem = 6 * TILE_BYTES + P_BYTES + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(space_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int grid = G.groups < num_sms() ? G.groups : num_sms();
+  space_attn_fwd_tc_kernel<<<grid, TC_THREADS, smem, st>>>(tm_rows, tm_cls, reinterpret_cast<bf16*>(out), lse, cls_part, G);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+}  // namespace egovlp
