@@ -26,7 +26,7 @@ constexpr int TILE_ROWS = 208;            // rows reserved per Q/K/V tile (NKP <
 constexpr int TILE_BYTES = TILE_ROWS * ROWB;
 constexpr int P_BLOCK_BYTES = 128 * ROWB; // one 64-key column block of P for 128 rows
 constexpr int P_BYTES = 4 * P_BLOCK_BYTES;
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 384;             // TMA, MMA, TMEM-alloc, spare + 8 softmax warps
 constexpr int S1_COL = 224, O_COL = 448;  // TMEM columns: S_0 at 0, S_1 at 224, O at 448 (NKP <= 224)
 
 struct TcGeom {
@@ -51,6 +51,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t ofull_bar = bars + 80;
   const uint32_t ofree_bar = bars + 88;
   const uint32_t tmem_slot = bars + 96;
+  const uint32_t xchg = bars + 128;          // 2 x [2][128] floats: row max / row sum exchange between column halves
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,12 +71,12 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       mbar_init(full_bar + 8 * i, 1);
       mbar_init(empty_bar + 8 * i, 1);
       mbar_init(sfull_bar + 8 * i, 1);
-      mbar_init(sfree_bar + 8 * i, 4);
+      mbar_init(sfree_bar + 8 * i, 8);
     }
-    mbar_init(pready_bar, 4);
+    mbar_init(pready_bar, 8);
     mbar_init(pfree_bar, 1);
     mbar_init(ofull_bar, 1);
-    mbar_init(ofree_bar, 4);
+    mbar_init(ofree_bar, 8);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -146,10 +147,17 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       }
     }
   } else if (warp >= 4) {
-    // ======================= softmax + epilogue: one thread per query row =======================
-    const int qd = warp & 3;
+    // ======================= softmax + epilogue: TWO threads per query row =======================
+    // warps 4-7 take the first half of the key columns, warps 8-11 the second half of the same TMEM lanes; each
+    // thread keeps its half row (up to 112 fp32) in registers, so S is read from TMEM once; the two halves exchange
+    // their max / sum through smem and a 64-thread named barrier.
+    const int qd = warp & 3, half = (warp - 4) >> 2;
     const int r_in_tile = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const int HW = ((G.NKP / 8 + 1) / 2) * 8;             // columns per half, multiple of 8 (104 for 208)
+    const int col0 = half * HW, ncol = half ? G.NKP - HW : HW;
+    float* xmax = reinterpret_cast<float*>(gen + (xchg - base));      // [2][128]
+    float* xsum = xmax + 256;
     int it = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++it) {
       const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
@@ -158,73 +166,58 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const int row = t * 128 + r_in_tile;             // query row of the group (N = CLS query)
         const bool is_cls_q = row == G.N;
         // the CLS key (column N) is visible to every patch query, and to the CLS query in the first frame only
-        const int ncols = (is_cls_q && f != 0) ? G.N : G.NK;
-        const uint32_t s_addr = tmem + lane_base + (t ? S1_COL : 0);
+        const int vis = (is_cls_q && f != 0) ? G.N : G.NK;
+        const uint32_t s_addr = tmem + lane_base + (t ? S1_COL : 0) + col0;
         mbar_wait(sfull_bar + 8 * t, it & 1);
         tc_fence_after();
-        // pass 1: row max
+        uint32_t r[112];
+        tmem_ld_32x32b_x32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+        tmem_ld_32x32b_x32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+        tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
+        tmem_ld_32x32b_x16(s_addr + 96, *reinterpret_cast<uint32_t(*)[16]>(&r[96]));
+        tmem_ld_wait();
+        // S_t has been read by this warp: the MMA warp may overwrite it for the next group
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sfree_bar + 8 * t);
         float mx = -INFINITY;
-        for (int c0 = 0; c0 < G.NKP; c0 += 32) {
-          uint32_t r[32];
-          if (c0 + 32 <= G.NKP) {
-            tmem_ld_32x32b_x32(s_addr + c0, r);
-          } else {
-            uint32_t r16[16];
-            tmem_ld_32x32b_x16(s_addr + c0, r16);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0xff800000u; }
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (c0 + j < ncols) ? __uint_as_float(r[j]) : -INFINITY);
+        for (int j = 0; j < 112; ++j) {
+          const bool ok = j < ncol && col0 + j < vis;
+          r[j] = ok ? r[j] : 0xff800000u;
+          mx = fmaxf(mx, __uint_as_float(r[j]));
         }
+        xmax[half * 128 + r_in_tile] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        mx = fmaxf(mx, xmax[(half ^ 1) * 128 + r_in_tile]);
         const float ms = mx * LOG2E;
-        // pass 2: p = exp2(s*log2e - ms), row sum, bf16 P into the swizzled K-major smem tile
         mbar_wait(pfree_bar, (n & 1) ^ 1);               // the previous P V product has consumed the P tile
         float sum = 0.f;
-        for (int c0 = 0; c0 < G.NKP; c0 += 32) {
-          uint32_t r[32];
-          if (c0 + 32 <= G.NKP) {
-            tmem_ld_32x32b_x32(s_addr + c0, r);
-          } else {
-            uint32_t r16[16];
-            tmem_ld_32x32b_x16(s_addr + c0, r16);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0xff800000u; }
-          }
-          tmem_ld_wait();
-          float p[32];
+        for (int c = 0; c < 14; ++c) {
+          if (8 * c < ncol) {
+            float p[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            p[j] = (c0 + j < ncols) ? exp2f(__uint_as_float(r[j]) * LOG2E - ms) : 0.f;
-            sum += p[j];
-          }
-          const uint32_t blk = sP + (c0 >> 6) * P_BLOCK_BYTES + r_in_tile * ROWB;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c0 + 8 * c < G.NKP) {
-              const int chunk = ((c0 & 63) >> 3) + c;
-              const uint32_t a = blk + ((chunk ^ (r_in_tile & 7)) << 4);
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(p[8 * c], p[8 * c + 1])),
-                           "r"(pack_bf16x2(p[8 * c + 2], p[8 * c + 3])), "r"(pack_bf16x2(p[8 * c + 4], p[8 * c + 5])),
-                           "r"(pack_bf16x2(p[8 * c + 6], p[8 * c + 7])));
+            for (int j = 0; j < 8; ++j) {
+              p[j] = exp2f(__uint_as_float(r[8 * c + j]) * LOG2E - ms);
+              sum += p[j];
             }
+            const int col = col0 + 8 * c;
+            const uint32_t a = sP + (col >> 6) * P_BLOCK_BYTES + r_in_tile * ROWB + ((((col & 63) >> 3) ^ (r_in_tile & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(p[0], p[1])),
+                         "r"(pack_bf16x2(p[2], p[3])), "r"(pack_bf16x2(p[4], p[5])), "r"(pack_bf16x2(p[6], p[7])));
           }
         }
-        // S_t fully read -> the MMA warp may overwrite it for the next group; P_t written -> P V may start
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(sfree_bar + 8 * t);
-          mbar_arrive(pready_bar);
-        }
-        // epilogue: O row
+        xsum[half * 128 + r_in_tile] = sum;
+        fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the UMMA reads
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
+        sum += xsum[(half ^ 1) * 128 + r_in_tile];
+        if (lane == 0) mbar_arrive(pready_bar);
+        // epilogue: this thread's 32 columns of the O row
         mbar_wait(ofull_bar, n & 1);
         tc_fence_after();
-        uint32_t o[2][32];
-        tmem_ld_32x32b_x32(tmem + lane_base + O_COL, o[0]);
-        tmem_ld_32x32b_x32(tmem + lane_base + O_COL + 32, o[1]);
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(tmem + lane_base + O_COL + half * 32, o);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -232,22 +225,19 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         if (row < G.N) {
           const float inv = 1.f / sum;
           const long long tok = (long long)b * G.S + 1 + f * G.N + row;
-          uint4* dst = reinterpret_cast<uint4*>(out + tok * G.D + h * HD);
+          uint4* dst = reinterpret_cast<uint4*>(out + tok * G.D + h * HD + half * 32);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const uint32_t* s4 = &o[c >> 2][(c & 3) * 8];
-            dst[c] = make_uint4(pack_bf16x2(__uint_as_float(s4[0]) * inv, __uint_as_float(s4[1]) * inv),
-                                pack_bf16x2(__uint_as_float(s4[2]) * inv, __uint_as_float(s4[3]) * inv),
-                                pack_bf16x2(__uint_as_float(s4[4]) * inv, __uint_as_float(s4[5]) * inv),
-                                pack_bf16x2(__uint_as_float(s4[6]) * inv, __uint_as_float(s4[7]) * inv));
-          }
-          lse_out[((long long)(b * G.H + h)) * G.S + 1 + f * G.N + row] = mx + logf(sum);
+          for (int c = 0; c < 4; ++c)
+            dst[c] = make_uint4(pack_bf16x2(__uint_as_float(o[8 * c]) * inv, __uint_as_float(o[8 * c + 1]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * c + 2]) * inv, __uint_as_float(o[8 * c + 3]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
+                                pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
+          if (half == 0) lse_out[((long long)(b * G.H + h)) * G.S + 1 + f * G.N + row] = mx + logf(sum);
         } else if (is_cls_q) {
           float* dst = cls_part + (((long long)(b * G.H + h)) * G.T + f) * 66;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) dst[j] = __uint_as_float(o[j >> 5][j & 31]);
-          dst[64] = mx;
-          dst[65] = sum;
+          for (int j = 0; j < 32; ++j) dst[half * 32 + j] = __uint_as_float(o[j]);
+          if (half == 0) { dst[64] = mx; dst[65] = sum; }
         }
       }
     }
@@ -286,7 +276,7 @@ int space_attn_fwd_tc(const void* qkv, void* out, float* lse, float* cls_part, i
   if (rc) return rc;
   rc = make_tmap_nd_bf16(&tm_cls, qkv, 4, dims, strides, box_cls, true);
   if (rc) return rc;
-  const int smem = 6 * TILE_BYTES + P_BYTES + 256 + 1024;
+  const int smem = 6 * TILE_BYTES + P_BYTES + 128 + 2048 + 1024;
   static bool attr = false;
   if (!attr) {
     EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(space_attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
