@@ -48,14 +48,14 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t sfree_bar = bars + 48;      // 2
   const uint32_t pready_bar = bars + 64;
   const uint32_t pfree_bar = bars + 72;
-  const uint32_t ofull_bar = bars + 80;
-  const uint32_t ofree_bar = bars + 88;
-  const uint32_t tmem_slot = bars + 96;
+  const uint32_t ofull_bar = bars + 80;      // 2 (per query tile)
+  const uint32_t ofree_bar = bars + 96;      // O_0 region free (O_1 aliases S_0: released through sfree[0])
+  const uint32_t tmem_slot = bars + 104;
   const uint32_t xchg = bars + 128;          // 2 x [2][128] floats: row max / row sum exchange between column halves
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NT = (G.NK + 127) / 128;          // query tiles (1 or 2)
+  constexpr int NT = 2;                       // query tiles (the host only routes 128 < N+1 <= 208 here)
 
   // zero the padding rows NK .. TILE_ROWS-1 of every tile once (TMA never writes them): V pad rows must be finite
   for (int i = threadIdx.x; i < 6 * (TILE_ROWS - G.NK) * 8; i += TC_THREADS) {
@@ -76,6 +76,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     mbar_init(pready_bar, 8);
     mbar_init(pfree_bar, 1);
     mbar_init(ofull_bar, 1);
+    mbar_init(ofull_bar + 8, 1);
     mbar_init(ofree_bar, 8);
     fence_mbar_init();
   }
@@ -131,16 +132,19 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       for (int t = 0; t < NT; ++t) {
         const int n = it * NT + t;
         mbar_wait(pready_bar, n & 1);
-        mbar_wait(ofree_bar, (n & 1) ^ 1);
+        if (t == 0) mbar_wait(ofree_bar, (it & 1) ^ 1);         // O_0 of the previous group has been read
         tc_fence_after();
         if (lane == 0) {
+          // O_0 has its own columns; O_1 reuses the first columns of S_0, which every softmax warp read long ago
+          // (they signalled P_1 after it); the next group's S_0 waits for the O_1 epilogue through sfree[0]
+          const uint32_t o_tmem = tmem + (t == 0 ? O_COL : 0);
           for (int ks = 0; ks < G.NKP / 16; ++ks) {
             const uint64_t ad = make_smem_desc_sw128(sP + (ks >> 2) * P_BLOCK_BYTES + (ks & 3) * 32, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(v + ks * 16 * ROWB, 8192, 1024);
-            umma_bf16_ss(tmem + O_COL, ad, bd, idesc_o, ks > 0);
+            umma_bf16_ss(o_tmem, ad, bd, idesc_o, ks > 0);
           }
           umma_commit(pfree_bar);
-          umma_commit(ofull_bar);
+          umma_commit(ofull_bar + 8 * t);
           if (t == NT - 1) umma_commit(empty_bar + 8 * buf);     // every UMMA reading this Q/K/V buffer is done
         }
         __syncwarp();
@@ -161,12 +165,14 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     int it = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++it) {
       const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
-      for (int t = 0; t < NT; ++t) {
-        const int n = it * NT + t;
+      float mx0 = 0.f, mx1 = 0.f, sum0 = 0.f, sum1 = 0.f;
+      // ---- softmax of both query tiles first; their P V products run underneath, the O rows are read afterwards
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int n = it * 2 + t;
         const int row = t * 128 + r_in_tile;             // query row of the group (N = CLS query)
-        const bool is_cls_q = row == G.N;
         // the CLS key (column N) is visible to every patch query, and to the CLS query in the first frame only
-        const int vis = (is_cls_q && f != 0) ? G.N : G.NK;
+        const int vis = (row == G.N && f != 0) ? G.N : G.NK;
         const uint32_t s_addr = tmem + lane_base + (t ? S1_COL : 0) + col0;
         mbar_wait(sfull_bar + 8 * t, it & 1);
         tc_fence_after();
@@ -176,10 +182,11 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         tmem_ld_32x32b_x32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&r[64]));
         tmem_ld_32x32b_x16(s_addr + 96, *reinterpret_cast<uint32_t(*)[16]>(&r[96]));
         tmem_ld_wait();
-        // S_t has been read by this warp: the MMA warp may overwrite it for the next group
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sfree_bar + 8 * t);
+        if (t == 1) {           // S_1 is free again (S_0's columns stay reserved: O_1 lands there)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sfree_bar + 8);
+        }
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 112; ++j) {
@@ -209,19 +216,26 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           }
         }
         xsum[half * 128 + r_in_tile] = sum;
+        tc_fence_before();
         fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the UMMA reads
         asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
         sum += xsum[(half ^ 1) * 128 + r_in_tile];
         if (lane == 0) mbar_arrive(pready_bar);
-        // epilogue: this thread's 32 columns of the O row
-        mbar_wait(ofull_bar, n & 1);
+        if (t == 0) { mx0 = mx; sum0 = sum; } else { mx1 = mx; sum1 = sum; }
+      }
+      // ---- epilogues: this thread's 32 columns of each O row
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const int row = t * 128 + r_in_tile;
+        mbar_wait(ofull_bar + 8 * t, it & 1);
         tc_fence_after();
         uint32_t o[32];
-        tmem_ld_32x32b_x32(tmem + lane_base + O_COL + half * 32, o);
+        tmem_ld_32x32b_x32(tmem + lane_base + (t == 0 ? O_COL : 0) + half * 32, o);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(ofree_bar);
+        if (lane == 0) mbar_arrive(t == 0 ? ofree_bar : sfree_bar);   // O_1 read -> S_0's columns are free again
+        const float mx = t ? mx1 : mx0, sum = t ? sum1 : sum0;
         if (row < G.N) {
           const float inv = 1.f / sum;
           const long long tok = (long long)b * G.S + 1 + f * G.N + row;
@@ -233,7 +247,7 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
                                 pack_bf16x2(__uint_as_float(o[8 * c + 4]) * inv, __uint_as_float(o[8 * c + 5]) * inv),
                                 pack_bf16x2(__uint_as_float(o[8 * c + 6]) * inv, __uint_as_float(o[8 * c + 7]) * inv));
           if (half == 0) lse_out[((long long)(b * G.H + h)) * G.S + 1 + f * G.N + row] = mx + logf(sum);
-        } else if (is_cls_q) {
+        } else if (row == G.N) {
           float* dst = cls_part + (((long long)(b * G.H + h)) * G.T + f) * 66;
 #pragma unroll
           for (int j = 0; j < 32; ++j) dst[half * 32 + j] = __uint_as_float(o[j]);
