@@ -268,9 +268,13 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
 }  // namespace
 
 // geometry the tcgen05 kernel covers: two query tiles, keys padded to <= 208
+// Opt-in (EGOVLP_ATTN_TC=1).  Measured at B=16, T=16, N=196, H=12 (tools/bench_misc.py): this kernel 0.185 ms vs
+// 0.163 ms for the mma.sync span kernel -- at head_dim 64 and 197 keys the tcgen05 formulation is bound by
+// TMEM -> register reads of S (277 KB per group at ~64 B/clk/SM) and MUFU exp2, not by the MMAs, while mma.sync
+// keeps S in registers.  The default dispatch therefore stays on the span kernel; see DESIGN.md section 7.
 bool space_attn_tc_supported(int N) {
   const char* e = getenv("EGOVLP_ATTN_TC");
-  if (e && e[0] == '0') return false;
+  if (!(e && e[0] == '1')) return false;
   const int NK = N + 1;
   return NK > 128 && NK <= TILE_ROWS;
 }
