@@ -738,17 +738,31 @@ __device__ __forceinline__ void fwd_chunk(const FastCtx& c, const Smem& sm, cons
   const float ms0 = (mn0 == -INFINITY) ? 0.f : mn0 * LOG2E, ms1 = (mn1 == -INFINITY) ? 0.f : mn1 * LOG2E;
   const float a0 = exp2f(m0 * LOG2E - ms0), a1 = exp2f(m1 * LOG2E - ms1);
   m0 = mn0; m1 = mn1;
-  l0 *= a0; l1 *= a1;
+  // packed fp32x2 (FFMA2 / FMUL2 / FADD2): the softmax bookkeeping is issue-bound next to the mma stream
+  const f32x2 av0 = pk2(a0, a0), av1 = pk2(a1, a1);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1; }
+  for (int j = 0; j < 8; ++j) {
+    up2(mul2(pk2(o[j][0], o[j][1]), av0), o[j][0], o[j][1]);
+    up2(mul2(pk2(o[j][2], o[j][3]), av1), o[j][2], o[j][3]);
+  }
+  const f32x2 sc = pk2(LOG2E, LOG2E), nm0 = pk2(-ms0, -ms0), nm1 = pk2(-ms1, -ms1);
+  f32x2 la0 = pk2(l0 * a0, 0.f), la1 = pk2(l1 * a1, 0.f);
   uint32_t pf[NPR][4];
 #pragma unroll
   for (int j = 0; j < 2 * NPR; ++j) {
-    const float p0 = exp2f(s[j][0] * LOG2E - ms0), p1 = exp2f(s[j][1] * LOG2E - ms0);
-    const float p2 = exp2f(s[j][2] * LOG2E - ms1), p3 = exp2f(s[j][3] * LOG2E - ms1);
-    l0 += p0 + p1; l1 += p2 + p3;
+    float e0, e1, e2, e3;
+    up2(fma2(pk2(s[j][0], s[j][1]), sc, nm0), e0, e1);
+    up2(fma2(pk2(s[j][2], s[j][3]), sc, nm1), e2, e3);
+    const float p0 = exp2f(e0), p1 = exp2f(e1), p2 = exp2f(e2), p3 = exp2f(e3);
+    la0 = add2(la0, pk2(p0, p1));
+    la1 = add2(la1, pk2(p2, p3));
     pf[j >> 1][(j & 1) * 2] = pack_bf16x2(p0, p1);
     pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p2, p3);
+  }
+  {
+    float x, y;
+    up2(la0, x, y); l0 = x + y;
+    up2(la1, x, y); l1 = x + y;
   }
 #pragma unroll
   for (int p = 0; p < NPR; ++p) {
@@ -858,23 +872,28 @@ __device__ __forceinline__ void bwd_q_chunk(const FastCtx& c, const Smem& sm, co
     }
   }
   uint32_t dsf[NPR][4];
+  const f32x2 sc = pk2(LOG2E, LOG2E), nl0 = pk2(-ls0, -ls0), nl1 = pk2(-ls1, -ls1);
+  const f32x2 nd0 = pk2(-de0, -de0), nd1 = pk2(-de1, -de1);
 #pragma unroll
   for (int p = 0; p < NPR; ++p) {
     const bool masked = ch.mask & (1u << p);
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;
-      bool v0 = true, v1 = true, v2 = true, v3 = true;
-      if (masked) {
-        v0 = fast_valid<TIME>(c, rowA, col); v1 = fast_valid<TIME>(c, rowA, col + 1);
-        v2 = fast_valid<TIME>(c, rowB, col); v3 = fast_valid<TIME>(c, rowB, col + 1);
+      if (masked) {               // exp2(-inf) = 0: masked entries drop out of P and dS
+        s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
+        s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
+        s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
+        s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
       }
-      const float p0 = v0 ? exp2f(s[j][0] * LOG2E - ls0) : 0.f;
-      const float p1 = v1 ? exp2f(s[j][1] * LOG2E - ls0) : 0.f;
-      const float p2 = v2 ? exp2f(s[j][2] * LOG2E - ls1) : 0.f;
-      const float p3 = v3 ? exp2f(s[j][3] * LOG2E - ls1) : 0.f;
-      dsf[p][jj * 2] = pack_bf16x2(p0 * (dp[j][0] - de0), p1 * (dp[j][1] - de0));
-      dsf[p][jj * 2 + 1] = pack_bf16x2(p2 * (dp[j][2] - de1), p3 * (dp[j][3] - de1));
+      float e0, e1, e2, e3;
+      up2(fma2(pk2(s[j][0], s[j][1]), sc, nl0), e0, e1);
+      up2(fma2(pk2(s[j][2], s[j][3]), sc, nl1), e2, e3);
+      float d0, d1, d2, d3;
+      up2(mul2(pk2(exp2f(e0), exp2f(e1)), add2(pk2(dp[j][0], dp[j][1]), nd0)), d0, d1);
+      up2(mul2(pk2(exp2f(e2), exp2f(e3)), add2(pk2(dp[j][2], dp[j][3]), nd1)), d2, d3);
+      dsf[p][jj * 2] = pack_bf16x2(d0, d1);
+      dsf[p][jj * 2 + 1] = pack_bf16x2(d2, d3);
     }
   }
 #pragma unroll
@@ -914,27 +933,33 @@ __device__ __forceinline__ void bwd_k_chunk(const FastCtx& c, const Smem& sm, co
     }
   }
   uint32_t pf[NPR][4], dsf[NPR][4];
+  const f32x2 sc = pk2(LOG2E, LOG2E);
 #pragma unroll
   for (int p = 0; p < NPR; ++p) {
     const bool masked = ch.mask & (1u << p);
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
       const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;       // query index
-      bool v0 = true, v1 = true, v2 = true, v3 = true;
       if (masked) {
-        v0 = fast_valid<TIME>(c, col, keyA); v1 = fast_valid<TIME>(c, col + 1, keyA);
-        v2 = fast_valid<TIME>(c, col, keyB); v3 = fast_valid<TIME>(c, col + 1, keyB);
+        st[j][0] = fast_valid<TIME>(c, col, keyA) ? st[j][0] : -INFINITY;
+        st[j][1] = fast_valid<TIME>(c, col + 1, keyA) ? st[j][1] : -INFINITY;
+        st[j][2] = fast_valid<TIME>(c, col, keyB) ? st[j][2] : -INFINITY;
+        st[j][3] = fast_valid<TIME>(c, col + 1, keyB) ? st[j][3] : -INFINITY;
       }
       const float2 lq = *reinterpret_cast<const float2*>(sm.lse + col);
       const float2 dq2 = *reinterpret_cast<const float2*>(sm.delta + col);
-      const float p0 = v0 ? exp2f(st[j][0] * LOG2E - lq.x) : 0.f;
-      const float p1 = v1 ? exp2f(st[j][1] * LOG2E - lq.y) : 0.f;
-      const float p2 = v2 ? exp2f(st[j][2] * LOG2E - lq.x) : 0.f;
-      const float p3 = v3 ? exp2f(st[j][3] * LOG2E - lq.y) : 0.f;
+      const f32x2 nl = pk2(-lq.x, -lq.y), nd = pk2(-dq2.x, -dq2.y);
+      float e0, e1, e2, e3;
+      up2(fma2(pk2(st[j][0], st[j][1]), sc, nl), e0, e1);
+      up2(fma2(pk2(st[j][2], st[j][3]), sc, nl), e2, e3);
+      const float p0 = exp2f(e0), p1 = exp2f(e1), p2 = exp2f(e2), p3 = exp2f(e3);
       pf[p][jj * 2] = pack_bf16x2(p0, p1);
       pf[p][jj * 2 + 1] = pack_bf16x2(p2, p3);
-      dsf[p][jj * 2] = pack_bf16x2(p0 * (dpt[j][0] - dq2.x), p1 * (dpt[j][1] - dq2.y));
-      dsf[p][jj * 2 + 1] = pack_bf16x2(p2 * (dpt[j][2] - dq2.x), p3 * (dpt[j][3] - dq2.y));
+      float d0, d1, d2, d3;
+      up2(mul2(pk2(p0, p1), add2(pk2(dpt[j][0], dpt[j][1]), nd)), d0, d1);
+      up2(mul2(pk2(p2, p3), add2(pk2(dpt[j][2], dpt[j][3]), nd)), d2, d3);
+      dsf[p][jj * 2] = pack_bf16x2(d0, d1);
+      dsf[p][jj * 2 + 1] = pack_bf16x2(d2, d3);
     }
   }
 #pragma unroll

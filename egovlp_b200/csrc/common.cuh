@@ -76,6 +76,33 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
 }
 
 // ------------------------------------------------------------------------------------------
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2 -- two fp32 lanes per instruction; issue-bound
+// epilogues and softmax loops use it to halve their FMA-pipe instruction count)
+// ------------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void up2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -84,6 +84,38 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
 }
 
+// Two elements per instruction on the FMA pipe (FFMA2): cdf = 0.5 (1 + erf(x/sqrt2)), pdf-term e = exp(-x^2/2).
+__device__ __forceinline__ void gelu_parts2(float x0, float x1, f32x2& cdf, f32x2& e2, f32x2& x2) {
+  x2 = pk2(x0, x1);
+  const f32x2 sq = mul2(x2, x2);
+  float s0, s1;
+  up2(mul2(sq, pk2(-0.72134752044448170f, -0.72134752044448170f)), s0, s1);      // -0.5 * log2(e) * x^2
+  const float e0 = exp2f(s0), e1 = exp2f(s1);
+  e2 = pk2(e0, e1);
+  const f32x2 z = mul2(pk2(fabsf(x0), fabsf(x1)), pk2(0.70710678118654752f, 0.70710678118654752f));
+  float d0, d1;
+  up2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.f, 1.f)), d0, d1);
+  const f32x2 t = pk2(__frcp_rn(d0), __frcp_rn(d1));
+  f32x2 p = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, pk2(0.254829592f, 0.254829592f));
+  p = mul2(p, t);
+  float a0, a1;
+  up2(fma2(mul2(p, e2), pk2(-1.f, -1.f), pk2(1.f, 1.f)), a0, a1);                   // erf(|x|/sqrt2)
+  cdf = fma2(pk2(copysignf(a0, x0), copysignf(a1, x1)), pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));
+}
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  f32x2 cdf, e2, x2;
+  gelu_parts2(x0, x1, cdf, e2, x2);
+  up2(mul2(x2, cdf), x0, x1);
+}
+__device__ __forceinline__ void gelu_grad_fast2(float u0, float u1, float& g0, float& g1) {
+  f32x2 cdf, e2, x2;
+  gelu_parts2(u0, u1, cdf, e2, x2);
+  up2(fma2(mul2(x2, e2), pk2(0.3989422804014327f, 0.3989422804014327f), cdf), g0, g1);
+}
+
 // Epilogue staging (warp-private, 32 rows x 128 B).  bf16: a row's 32 values = 4 x 16B chunks placed at slot
 // (c ^ ((r>>1)&3)) + 4*(r&1) so that both the row-owner writes and the 4-lanes-per-row reads are conflict-free.
 __device__ __forceinline__ void stage_bf16_rows(uint32_t stg, int lane, const float (&v)[32]) {
@@ -283,14 +315,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         const int n0 = n_blk * BLOCK_N + half * COLS_PER_WARP + c;
         if (n0 >= N) continue;     // warp-uniform
         float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
-        if (ep.bias) {
+        {
+          const f32x2 al = pk2(ep.alpha, ep.alpha);
           const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            const float4 b = ep.bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            up2(fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), al, pk2(b.x, b.y)), v[4 * j], v[4 * j + 1]);
+            up2(fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), al, pk2(b.z, b.w)), v[4 * j + 2],
+                v[4 * j + 3]);
           }
         }
         if (n0 < ep.col_scale_ncols) {
@@ -305,7 +338,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if (ep.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < 32; j += 2) gelu_fast2(v[j], v[j + 1]);
         }
         const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.colsum != nullptr;
         if (!wide) {
@@ -342,8 +375,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
             if (ep.act == 2) {
               const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
-              x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
-              x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
+              float g0, g1, g2, g3;
+              gelu_grad_fast2(p0.x, p0.y, g0, g1);
+              gelu_grad_fast2(p1.x, p1.y, g2, g3);
+              x.x *= g0; x.y *= g1; x.z *= g2; x.w *= g3;
             }
             if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
             if (grow < M) {
