@@ -66,54 +66,31 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7): 2 MUFU + ~10 FMA per element instead of erff's ~30
-// instructions -- the GELU epilogue has to finish inside the 6144-cycle MMA time of a K=768 tile.
-__device__ __forceinline__ float erf_abs_fast(float z, float e) {   // z >= 0, e = exp(-z*z)
-  const float t = 1.f / (1.f + 0.3275911f * z);
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  return 1.f - poly * e;
+// GELU (exact-erf form) in the epilogue.  Phi(x) = 0.5 (1 + erf(x / sqrt2)) through Abramowitz-Stegun 7.1.26
+// (|err| <= 1.5e-7 on erf): with t = 1 / (1 + p |x| / sqrt2) and e = exp(-x^2 / 2),
+//     q = 0.5 (1 - erf(|x| / sqrt2)) = e * t * (a1' + t (a2' + t (a3' + t (a4' + t a5'))))      (a' = a / 2)
+//     Phi(x) = x >= 0 ? 1 - q : q
+// = 2 MUFU + 11 FMA-pipe instructions per element (erff is ~30): the fc1 epilogue is issue-bound -- it has to fit in
+// the 6144-cycle MMA time of a K = 768 tile -- so constants are folded wherever a multiply would only rescale.
+__device__ __forceinline__ float gelu_q(float x, float& e) {
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.f)));
+  e = exp2f(x * x * -0.72134752044448170f);            // exp(-x^2 / 2)
+  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
+  return p * t * e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float e = __expf(-0.5f * x * x);
-  const float er = copysignf(erf_abs_fast(fabsf(x) * 0.70710678118654752f, e), x);
-  return 0.5f * x * (1.f + er);
+  float e;
+  const float xq = x * gelu_q(x, e);
+  return x >= 0.f ? x - xq : xq;
 }
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float e = __expf(-0.5f * x * x);
-  const float er = copysignf(erf_abs_fast(fabsf(x) * 0.70710678118654752f, e), x);
-  return 0.5f * (1.f + er) + x * 0.3989422804014327f * e;
-}
-
-// Two elements per instruction on the FMA pipe (FFMA2): cdf = 0.5 (1 + erf(x/sqrt2)), pdf-term e = exp(-x^2/2).
-__device__ __forceinline__ void gelu_parts2(float x0, float x1, f32x2& cdf, f32x2& e2, f32x2& x2) {
-  x2 = pk2(x0, x1);
-  const f32x2 sq = mul2(x2, x2);
-  float s0, s1;
-  up2(mul2(sq, pk2(-0.72134752044448170f, -0.72134752044448170f)), s0, s1);      // -0.5 * log2(e) * x^2
-  const float e0 = exp2f(s0), e1 = exp2f(s1);
-  e2 = pk2(e0, e1);
-  const f32x2 z = mul2(pk2(fabsf(x0), fabsf(x1)), pk2(0.70710678118654752f, 0.70710678118654752f));
-  float d0, d1;
-  up2(fma2(z, pk2(0.3275911f, 0.3275911f), pk2(1.f, 1.f)), d0, d1);
-  const f32x2 t = pk2(__frcp_rn(d0), __frcp_rn(d1));
-  f32x2 p = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
-  p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
-  p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
-  p = fma2(p, t, pk2(0.254829592f, 0.254829592f));
-  p = mul2(p, t);
-  float a0, a1;
-  up2(fma2(mul2(p, e2), pk2(-1.f, -1.f), pk2(1.f, 1.f)), a0, a1);                   // erf(|x|/sqrt2)
-  cdf = fma2(pk2(copysignf(a0, x0), copysignf(a1, x1)), pk2(0.5f, 0.5f), pk2(0.5f, 0.5f));
-}
-__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
-  f32x2 cdf, e2, x2;
-  gelu_parts2(x0, x1, cdf, e2, x2);
-  up2(mul2(x2, cdf), x0, x1);
-}
-__device__ __forceinline__ void gelu_grad_fast2(float u0, float u1, float& g0, float& g1) {
-  f32x2 cdf, e2, x2;
-  gelu_parts2(u0, u1, cdf, e2, x2);
-  up2(fma2(mul2(x2, e2), pk2(0.3989422804014327f, 0.3989422804014327f), cdf), g0, g1);
+__device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
+  float e;
+  const float q = gelu_q(x, e);
+  return fmaf(x * 0.3989422804014327f, e, x >= 0.f ? 1.f - q : q);
 }
 
 // Epilogue staging (warp-private, 32 rows x 128 B).  bf16: a row's 32 values = 4 x 16B chunks placed at slot
@@ -338,7 +315,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         if (ep.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) gelu_fast2(v[j], v[j + 1]);
+          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
         }
         const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.colsum != nullptr;
         if (!wide) {
@@ -375,10 +352,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
             if (ep.act == 2) {
               const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
-              float g0, g1, g2, g3;
-              gelu_grad_fast2(p0.x, p0.y, g0, g1);
-              gelu_grad_fast2(p1.x, p1.y, g2, g3);
-              x.x *= g0; x.y *= g1; x.z *= g2; x.w *= g3;
+              x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
+              x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
             }
             if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
             if (grow < M) {

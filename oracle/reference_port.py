@@ -133,7 +133,7 @@ def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_mode
     d = D // heads
     x = we[input_ids] + pe[:L].unsqueeze(0)
     x = F.layer_norm(x, (D,), p[prefix + "embeddings.LayerNorm.weight"], p[prefix + "embeddings.LayerNorm.bias"], eps)
-    key_bias = torch.zeros(B, 1, 1, L, dtype=x.dtype)
+    key_bias = torch.zeros(B, 1, 1, L, dtype=x.dtype, device=x.device)
     key_bias = key_bias.masked_fill(attention_mask.reshape(B, 1, 1, L) == 0, float("-inf"))
     n_layers = 1 + max(int(k.split("transformer.layer.")[1].split(".")[0]) for k in p if "transformer.layer." in k)
     for i in range(n_layers):
@@ -207,7 +207,7 @@ def egonce_loss(x, sim_v, sim_n, temperature=0.05, noun=True, verb=True):
     """EgoNCE.forward (model/loss.py:34-53).  Positives: diagonal plus pairs whose
     verb AND noun similarity products are > 0 (variants via the noun/verb flags, :36-41).
     Note the column term reuses the un-transposed mask (:50), restated as is."""
-    eye = torch.eye(x.shape[0], dtype=x.dtype)
+    eye = torch.eye(x.shape[0], dtype=x.dtype, device=x.device)
     if noun and verb:
         mask = sim_v * sim_n + eye
     elif noun:
@@ -226,7 +226,7 @@ def max_margin_ranking_loss(x, margin=0.2, fix_norm=True):
     d = x.diagonal().unsqueeze(1)
     h = torch.relu(margin - (d - x)) + torch.relu(margin - (d - x.t()))   # [i,j]: rows, and columns of x
     if fix_norm:
-        off = 1.0 - torch.eye(n, dtype=x.dtype)
+        off = 1.0 - torch.eye(n, dtype=x.dtype, device=x.device)
         return (h * off).sum() / (2 * n * (n - 1))
     return h.sum() / (2 * n * n)
 
