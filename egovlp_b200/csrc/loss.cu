@@ -167,17 +167,19 @@ __global__ void nce_bwd_kernel(const float* __restrict__ x, const uint8_t* __res
   dx[idx] = -(gscale ? *gscale : 1.f) * inv_temp / G * t;
 }
 
-// MaxMarginRankingLoss: mean over (i != j if fix_norm) of relu(m - (x_ii - x_ij)) + relu(m - (x_ii - x_ji)), /2
-__global__ void maxmargin_fwd_kernel(const float* __restrict__ x, int G, float margin, int fix_norm,
-                                     float* __restrict__ loss) {
+// MaxMarginRankingLoss: mean over (i != j if fix_norm) of relu(m_i - (x_ii - x_ij)) + relu(m_i - (x_ii - x_ji)), /2.
+// m_i = margin (model/loss.py:63-90) or margin * weight[i] (AdaptiveMaxMarginRankingLoss, model/loss.py:100-133: the
+// weight is expanded along the row of the anchor i in BOTH directions).
+__global__ void maxmargin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ weight, int G, float margin,
+                                     int fix_norm, float* __restrict__ loss) {
   __shared__ float red[32];
   float s = 0.f;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < (long long)G * G;
        idx += (long long)gridDim.x * blockDim.x) {
     const int i = idx / G, j = idx % G;
     if (fix_norm && i == j) continue;
-    const float d = x[(long long)i * G + i];
-    s += fmaxf(0.f, margin - (d - x[idx])) + fmaxf(0.f, margin - (d - x[(long long)j * G + i]));
+    const float d = x[(long long)i * G + i], m = weight ? margin * weight[i] : margin;
+    s += fmaxf(0.f, m - (d - x[idx])) + fmaxf(0.f, m - (d - x[(long long)j * G + i]));
   }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -190,18 +192,18 @@ __global__ void maxmargin_fwd_kernel(const float* __restrict__ x, int G, float m
   }
 }
 // dx accumulated with atomics: each (i,j) term touches x_ii, x_ij, x_ji
-__global__ void maxmargin_bwd_kernel(const float* __restrict__ x, int G, float margin, int fix_norm,
-                                     const float* __restrict__ gscale, float* __restrict__ dx) {
+__global__ void maxmargin_bwd_kernel(const float* __restrict__ x, const float* __restrict__ weight, int G, float margin,
+                                     int fix_norm, const float* __restrict__ gscale, float* __restrict__ dx) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)G * G) return;
   const int i = idx / G, j = idx % G;
   if (fix_norm && i == j) return;
   const float denom = fix_norm ? 2.f * G * (G - 1) : 2.f * G * G;
   const float g = (gscale ? *gscale : 1.f) / denom;
-  const float d = x[(long long)i * G + i];
+  const float d = x[(long long)i * G + i], m = weight ? margin * weight[i] : margin;
   float dd = 0.f;
-  if (margin - (d - x[idx]) > 0.f) { atomicAdd(dx + idx, g); dd -= g; }
-  if (margin - (d - x[(long long)j * G + i]) > 0.f) { atomicAdd(dx + (long long)j * G + i, g); dd -= g; }
+  if (m - (d - x[idx]) > 0.f) { atomicAdd(dx + idx, g); dd -= g; }
+  if (m - (d - x[(long long)j * G + i]) > 0.f) { atomicAdd(dx + (long long)j * G + i, g); dd -= g; }
   if (dd != 0.f) atomicAdd(dx + (long long)i * G + i, dd);
 }
 
@@ -328,21 +330,22 @@ extern "C" int egovlp_nce_bwd(const float* x, const uint8_t* mask, const float* 
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
-extern "C" int egovlp_maxmargin_fwd(const float* x, int G, float margin, int fix_norm, float* loss, void* stream) {
+extern "C" int egovlp_maxmargin_fwd(const float* x, const float* row_weight, int G, float margin, int fix_norm,
+                                    float* loss, void* stream) {
   EGOVLP_CHECK_ARG(x && loss && G > 1, "maxmargin_fwd: bad args");
   EGOVLP_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
   const long long n = (long long)G * G;
   const int grid = (int)((n + 255) / 256 > 1024 ? 1024 : (n + 255) / 256);
-  maxmargin_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(x, G, margin, fix_norm, loss);
+  maxmargin_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(x, row_weight, G, margin, fix_norm, loss);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
-extern "C" int egovlp_maxmargin_bwd(const float* x, int G, float margin, int fix_norm, const float* gscale, float* dx,
-                                    void* stream) {
+extern "C" int egovlp_maxmargin_bwd(const float* x, const float* row_weight, int G, float margin, int fix_norm,
+                                    const float* gscale, float* dx, void* stream) {
   EGOVLP_CHECK_ARG(x && dx && G > 1, "maxmargin_bwd: bad args");
   const long long n = (long long)G * G;
   EGOVLP_CHECK_CUDA(cudaMemsetAsync(dx, 0, n * sizeof(float), ST(stream)));
-  maxmargin_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, G, margin, fix_norm, gscale, dx);
+  maxmargin_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(x, row_weight, G, margin, fix_norm, gscale, dx);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }

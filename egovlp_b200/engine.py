@@ -450,16 +450,21 @@ class NceLossFn(torch.autograd.Function):
 
 
 class MaxMarginFn(torch.autograd.Function):
-    """MaxMarginRankingLoss (model/loss.py:63-90), no host-side index building."""
+    """MaxMarginRankingLoss (model/loss.py:63-90) and, with `row_weight`, AdaptiveMaxMarginRankingLoss
+    (model/loss.py:100-133); no host-side index building.  The weight gets no gradient (the reference feeds the
+    dataset's relevancy, a constant)."""
 
     @staticmethod
-    def forward(ctx, x, margin, fix_norm):
+    def forward(ctx, x, margin, fix_norm, row_weight=None):
         x = x.contiguous().float()
+        w = None if row_weight is None else row_weight.detach().contiguous().float()
         ctx.args = (margin, fix_norm)
-        ctx.save_for_backward(x)
-        return ops.maxmargin_fwd(x, margin, fix_norm)
+        ctx.has_w = w is not None
+        ctx.save_for_backward(*((x, w) if w is not None else (x,)))
+        return ops.maxmargin_fwd(x, margin, fix_norm, w)
 
     @staticmethod
     def backward(ctx, g):
-        (x,) = ctx.saved_tensors
-        return ops.maxmargin_bwd(x, ctx.args[0], ctx.args[1], g.contiguous().float()), None, None
+        x = ctx.saved_tensors[0]
+        w = ctx.saved_tensors[1] if ctx.has_w else None
+        return ops.maxmargin_bwd(x, ctx.args[0], ctx.args[1], g.contiguous().float(), w), None, None, None

@@ -1,5 +1,5 @@
 """Losses of the reference's model/loss.py on CUDA kernels: same class names, constructor arguments and
-forward signatures.  AdaptiveMaxMarginRankingLoss / CrossEntropy are outside the hot-path scope."""
+forward signatures.  CrossEntropy (OSCC / PNR heads) is outside the hot-path scope."""
 import torch
 from torch import nn
 
@@ -48,4 +48,17 @@ class MaxMarginRankingLoss(nn.Module):
         self.fix_norm, self.margin = fix_norm, margin
 
     def forward(self, x, weight=None):
-        return engine.MaxMarginFn.apply(x, self.margin, self.fix_norm)
+        return engine.MaxMarginFn.apply(x, self.margin, self.fix_norm)       # `weight` ignored, as the reference (:63-90)
+
+
+class AdaptiveMaxMarginRankingLoss(nn.Module):
+    """model/loss.py:92-133: the margin of anchor i is `weight[i] * margin` (EPIC-MIR fine-tuning with relevancy)."""
+
+    def __init__(self, margin=0.4, fix_norm=True):
+        super().__init__()
+        self.fix_norm, self.margin = fix_norm, margin
+
+    def forward(self, x, weight=None):
+        if weight is None:
+            raise AttributeError("AdaptiveMaxMarginRankingLoss needs `weight` [n] (the reference calls weight.unsqueeze)")
+        return engine.MaxMarginFn.apply(x, self.margin, self.fix_norm, weight)

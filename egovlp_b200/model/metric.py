@@ -25,3 +25,61 @@ def egomcq_accuracy_metrics(preds, labels, types):
                 total += 1
         metrics[group_i] = correct / total * 100
     return metrics
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# EPIC-Kitchens-100 multi-instance retrieval (model/metric.py:236-299)
+# ------------------------------------------------------------------------------------------------------------------
+
+def initialise_nDCG_values(relevancy_matrix):
+    """model/metric.py:236-246."""
+    from ..utils import nDCG
+    rel = nDCG._rel(relevancy_matrix)
+    vis_k, txt_k = nDCG.calculate_k_counts(rel), nDCG.calculate_k_counts(rel.t().contiguous())
+    vis_IDCG, txt_IDCG = nDCG.calculate_IDCG(rel, vis_k), nDCG.calculate_IDCG(rel.t().contiguous(), txt_k)
+    return {"v": vis_IDCG, "t": txt_IDCG}, {"v": vis_k, "t": txt_k}
+
+
+def initialise_jpose_nDCG_values(relevancy_matrix):
+    """model/metric.py:248-255."""
+    idcg, k_values = initialise_nDCG_values(relevancy_matrix)
+    return {"action": {"IDCG": idcg, "k_values": k_values}}
+
+
+def mir_metrics_core(similarity_matrix, idx_arr, video_id, text_id, relevancy):
+    """model/metric.py:257-299 after the annotation files are read: `similarity_matrix` [N, N] cosine similarities of
+    text i vs video j in LOADER order, `idx_arr` [N] the dataset index of every loader position, `video_id` [N] /
+    `text_id` [Nt] the annotation id columns, `relevancy` [N, Nt].  Everything stays on the GPU."""
+    from ..utils import nDCG, mAP
+    sim = nDCG._dev(similarity_matrix, torch.float32)
+    sim = (sim + 1) / 2
+    video_id, idx_list = list(video_id), torch.as_tensor(idx_arr).tolist()
+    first = {}
+    for pos, v in enumerate(video_id):
+        first.setdefault(v, pos)
+    indexes = [first[e] for e in text_id if e in first]                  # :266-270 (`list.index` = first occurrence)
+    pos_of = {}
+    for pos, i in enumerate(idx_list):
+        pos_of.setdefault(i, pos)
+    order = torch.tensor([pos_of[i] for i in range(len(video_id))], device=sim.device)        # :272-275
+    sim = sim[order][:, order]
+    sim = sim.t()[:, torch.tensor(indexes, device=sim.device)].contiguous()                  # [videos, unique texts]
+    rel = nDCG._rel(relevancy)
+    sim_t, rel_t = sim.t().contiguous(), rel.t().contiguous()
+    vis_nDCG, txt_nDCG = nDCG.calculate_nDCG(sim, rel), nDCG.calculate_nDCG(sim_t, rel_t)
+    vis_mAP, txt_mAP = mAP.calculate_mAP(sim, rel), mAP.calculate_mAP(sim_t, rel_t)
+    return {"nDCG_V2T": vis_nDCG * 100, "nDCG_T2V": txt_nDCG * 100, "nDCG_AVG": 100 * (vis_nDCG + txt_nDCG) / 2,
+            "mAP_V2T": vis_mAP * 100, "mAP_T2V": txt_mAP * 100, "mAP_AVG": 100 * (vis_mAP + txt_mAP) / 2}
+
+
+def mir_metrics(similarity_matrix, idx_arr):
+    """Same contract as the reference (reads the EPIC annotation files from the same relative paths)."""
+    import os
+    import pickle
+    import pandas as pd
+    base = "dataset/epic-kitchens/epic-kitchens-100-annotations-master/retrieval_annotations"
+    video_id = pd.read_csv(os.path.join(base, "EPIC_100_retrieval_test.csv")).values[:, 0]
+    text_id = pd.read_csv(os.path.join(base, "EPIC_100_retrieval_test_sentence.csv")).values[:, 0]
+    with open(os.path.join(base, "relevancy/caption_relevancy_EPIC_100_retrieval_test.pkl"), "rb") as f:
+        relevancy = pickle.load(f)
+    return mir_metrics_core(similarity_matrix, idx_arr, video_id, text_id, relevancy)

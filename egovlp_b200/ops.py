@@ -283,16 +283,41 @@ def nce_bwd(x, mask, stats, inv_temp, gscale):
     return dx
 
 
-def maxmargin_fwd(x, margin, fix_norm):
+def maxmargin_fwd(x, margin, fix_norm, row_weight=None):
+    _chk(x, F32, "x")
+    if row_weight is not None:
+        _chk(row_weight, F32, "row_weight")
+        assert row_weight.shape == (x.shape[0],) and row_weight.is_contiguous()
     loss = torch.empty((), dtype=F32, device=x.device)
-    call("egovlp_maxmargin_fwd", _ptr(x), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(loss), _stream())
+    call("egovlp_maxmargin_fwd", _ptr(x), _ptr(row_weight), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(loss),
+         _stream())
     return loss
 
 
-def maxmargin_bwd(x, margin, fix_norm, gscale):
+def maxmargin_bwd(x, margin, fix_norm, gscale, row_weight=None):
     dx = torch.empty_like(x)
-    call("egovlp_maxmargin_bwd", _ptr(x), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(gscale), _ptr(dx), _stream())
+    call("egovlp_maxmargin_bwd", _ptr(x), _ptr(row_weight), x.shape[0], C.c_float(margin), int(fix_norm), _ptr(gscale),
+         _ptr(dx), _stream())
     return dx
+
+
+def rank_metrics(sim, rel, k_counts=None, tie_mode=0, want_dcg=True, want_ap=True):
+    """Per-query ranking metrics (egovlp_rank_metrics): sim fp32 [R, C], rel fp32/fp64 [R, C], optional int32
+    k_counts [R, C] -> (dcg fp64 [R] | None, ap fp64 [R] | None)."""
+    _chk(sim, F32, "sim")
+    assert rel.is_cuda and rel.dtype in (torch.float32, torch.float64) and rel.shape == sim.shape and sim.dim() == 2
+    sim, rel = sim.contiguous(), rel.contiguous()
+    R, Cc = sim.shape
+    if k_counts is not None:
+        assert k_counts.is_cuda and k_counts.shape == sim.shape
+        k_counts = k_counts.to(torch.int32).contiguous()
+    dcg = torch.empty(R, dtype=torch.float64, device=sim.device) if want_dcg else None
+    ap = torch.empty(R, dtype=torch.float64, device=sim.device) if want_ap else None
+    if R == 0:
+        return dcg, ap
+    call("egovlp_rank_metrics", _ptr(sim), C.c_longlong(sim.stride(0)), _ptr(rel), int(rel.dtype == torch.float64),
+         C.c_longlong(rel.stride(0)), _ptr(k_counts), R, Cc, int(tie_mode), _ptr(dcg), _ptr(ap), _stream())
+    return dcg, ap
 
 
 def dual_softmax(sim, temp=500.0):

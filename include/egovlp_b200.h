@@ -154,8 +154,9 @@ int egovlp_relu_rows_bwd(const float* x, long long row_stride, const float* dh, 
  *               (sim_v*sim_n + I) > 0 for 0/1 tags;  mask_from_sims: the reference's float formulation itself.
  *   nce_fwd   : stats fp32 [4G] (row/col log-sum-exp over all / over positives of x*inv_temp), loss scalar
  *   nce_bwd   : dx fp32 [G,G] = gscale[0] * dloss/dx   (gscale device pointer or NULL for 1)
- *   maxmargin_fwd/bwd, dual_softmax (in: sim [rows, cols] -> out), egomcq_score (scores [Q,K], pred int64 [Q],
- *               ties -> lowest index).
+ *   maxmargin_fwd/bwd : MaxMarginRankingLoss (model/loss.py:63-90); row_weight fp32 [G] or NULL -- with it the margin
+ *               of anchor i is margin*row_weight[i] = AdaptiveMaxMarginRankingLoss (model/loss.py:100-133)
+ *   dual_softmax (in: sim [rows, cols] -> out), egomcq_score (scores [Q,K], pred int64 [Q], ties -> lowest index).
  */
 int egovlp_rownorm_fwd(const float* a, float* an, float* norm, int rows, int C, float eps, void* stream);
 int egovlp_rownorm_bwd(const float* dan, const float* an, const float* norm, float* da, int rows, int C, float eps,
@@ -169,12 +170,28 @@ int egovlp_mask_from_sims(const float* sim_v, const float* sim_n, uint8_t* mask,
 int egovlp_nce_fwd(const float* x, const uint8_t* mask, int G, float inv_temp, float* stats, float* loss, void* stream);
 int egovlp_nce_bwd(const float* x, const uint8_t* mask, const float* stats, int G, float inv_temp, const float* gscale,
                    float* dx, void* stream);
-int egovlp_maxmargin_fwd(const float* x, int G, float margin, int fix_norm, float* loss, void* stream);
-int egovlp_maxmargin_bwd(const float* x, int G, float margin, int fix_norm, const float* gscale, float* dx,
+int egovlp_maxmargin_fwd(const float* x, const float* row_weight, int G, float margin, int fix_norm, float* loss,
                          void* stream);
+int egovlp_maxmargin_bwd(const float* x, const float* row_weight, int G, float margin, int fix_norm,
+                         const float* gscale, float* dx, void* stream);
 int egovlp_dual_softmax(const float* sim, float* out, int rows, int cols, float temp, void* stream);
 int egovlp_egomcq_score(const float* text, const float* video, float* scores, long long* pred, int Q, int K, int C,
                         float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Retrieval evaluation (EPIC-Kitchens MIR).  Replaces the host numpy argsort + fancy indexing of
+ * utils/nDCG.py:3-45 (calculate_DCG) and utils/mAP.py:4-44 (calculate_mAP) called from model/metric.py:257-299 and
+ * run/test_epic.py:137-157.  One CTA ranks one query row in shared memory (bitonic sort of (similarity, column)).
+ *   sim  fp32 [rows, cols] (row stride ld_sim);  rel fp32 or fp64 [rows, cols] (row stride ld_rel)
+ *   k_counts int32 [rows, cols] contiguous or NULL (NULL: the first k ranks count, k = #(rel[row] > 0), which is what
+ *            calculate_k_counts, nDCG.py:47-75, produces)
+ *   tie_mode 0: equal similarities rank by smaller column first (stable argsort of -sim, mAP.py:25);
+ *            1: by larger column first (stable ascending argsort reversed, nDCG.py:32)
+ *   dcg[row] = sum_i k_i * rel[row, rank_i] / log2(i + 2);  ap[row] = sum_i [rel_i == 1] cumsum(rel)_i / (i + 1) / #(rel == 1)
+ *            (NaN for a row without relevant items, as numpy).  Either output may be NULL.  cols <= 16384.
+ */
+int egovlp_rank_metrics(const float* sim, long long ld_sim, const void* rel, int rel_is_f64, long long ld_rel,
+                        const int* k_counts, int rows, int cols, int tie_mode, double* dcg, double* ap, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Elementwise / reduction helpers on the path.

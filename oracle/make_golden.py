@@ -125,10 +125,77 @@ def full_cfg1():
     npz("full_cfg1.npz", text_emb=text_emb, video_emb=video_emb, sim=x, infonce=loss, seed=0, **sel, **gnorm)
 
 
+def retrieval():
+    """EPIC-MIR side: AdaptiveMaxMarginRankingLoss, utils/nDCG.py, utils/mAP.py and the whole
+    model/metric.py:mir_metrics flow (run on tiny annotation files written to a temp dir with the paths it expects)."""
+    import pickle
+    import tempfile
+    mm, _, ml = ref_shim.modules()
+    import model.metric as ref_metric
+    from utils import nDCG as ref_ndcg, mAP as ref_map
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    n = 12
+    x = torch.randn(n, n, generator=g) * 0.3
+    w = torch.rand(n, generator=g)
+    x_req = x.clone().requires_grad_(True)
+    l = ml.AdaptiveMaxMarginRankingLoss(margin=0.4, fix_norm=True)(x_req, w)
+    l.backward()
+    out.update(amm_x=x, amm_w=w, amm=l, amm_dx=x_req.grad,
+               amm_nofix=ml.AdaptiveMaxMarginRankingLoss(margin=0.4, fix_norm=False)(x, w))
+    # ranking metrics on tie-free similarities; graded relevancy in {0, .25, .5, 1}, every row has a 1
+    rng = np.random.default_rng(5)
+    R, Cc = 9, 700
+    sim = rng.permutation(R * Cc).reshape(R, Cc).astype(np.float32) / (R * Cc)
+    rel = rng.choice([0.0, 0.0, 0.0, 0.25, 0.5, 1.0], size=(R, Cc))
+    rel[np.arange(R), rng.integers(0, Cc, R)] = 1.0
+    kc = ref_ndcg.calculate_k_counts(rel)
+    out.update(rk_sim=sim, rk_rel=rel, rk_kcounts=kc, rk_dcg=ref_ndcg.calculate_DCG(sim, rel, kc),
+               rk_idcg=ref_ndcg.calculate_IDCG(rel, kc), rk_ndcg=ref_ndcg.calculate_nDCG(sim, rel),
+               rk_ndcg_vec=ref_ndcg.calculate_nDCG(sim, rel, reduction=None),
+               rk_ndcg_t=ref_ndcg.calculate_nDCG(sim.T, rel.T), rk_map=ref_map.calculate_mAP(sim, rel),
+               rk_map_t=ref_map.calculate_mAP(sim.T, rel.T))
+    # the reference's own known-answer example (utils/nDCG.py:141-164)
+    ka_sim = np.array([[1.0, 0.7, 0.4, 0.0], [0.3, 0.9, 0.6, 0.1], [0.2, 0.5, 0.8, 0.4]], dtype=np.float32)
+    ka_rel = np.array([[1.0, 0.5, 0.0, 0.0], [0.0, 1.0, 0.5, 0.0], [0.0, 0.0, 1.0, 0.5]])
+    out.update(ka_sim=ka_sim, ka_rel=ka_rel, ka_ndcg=ref_ndcg.calculate_nDCG(ka_sim, ka_rel),
+               ka_map=ref_map.calculate_mAP(ka_sim, ka_rel))
+    # full mir_metrics flow: N videos in shuffled loader order, Nt unique sentences
+    N, Nt = 40, 17
+    video_id = np.array([f"P{i:02d}_{i % 7}" for i in range(N)], dtype=object)
+    text_rows = np.sort(rng.choice(N, Nt, replace=False))
+    text_id = video_id[text_rows]
+    relevancy = rng.choice([0.0, 0.0, 0.3, 1.0], size=(N, Nt))
+    relevancy[text_rows, np.arange(Nt)] = 1.0
+    relevancy[np.arange(N), rng.integers(0, Nt, N)] = 1.0
+    idx_arr = torch.from_numpy(rng.permutation(N))
+    t_emb = torch.randn(N, 16, generator=g)
+    v_emb = torch.randn(N, 16, generator=g)
+    sims = mm.sim_matrix(t_emb, v_emb).numpy()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        base = os.path.join(tmp, "dataset/epic-kitchens/epic-kitchens-100-annotations-master/retrieval_annotations")
+        os.makedirs(os.path.join(base, "relevancy"))
+        import pandas as pd
+        pd.DataFrame({"narration_id": video_id}).to_csv(os.path.join(base, "EPIC_100_retrieval_test.csv"), index=False)
+        pd.DataFrame({"narration_id": text_id}).to_csv(os.path.join(base, "EPIC_100_retrieval_test_sentence.csv"), index=False)
+        with open(os.path.join(base, "relevancy/caption_relevancy_EPIC_100_retrieval_test.pkl"), "wb") as f:
+            pickle.dump(relevancy, f)
+        os.chdir(tmp)
+        try:
+            res = ref_metric.mir_metrics(sims, idx_arr)
+        finally:
+            os.chdir(cwd)
+    print("mir_metrics (reference):", res)
+    out.update(mir_sims=sims, mir_idx=idx_arr, mir_video_id=video_id.astype(str), mir_text_id=text_id.astype(str),
+               mir_relevancy=relevancy, **{"mir_" + k: v for k, v in res.items()})
+    npz("retrieval.npz", **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["video_tiny", "distilbert_tiny", "losses", "full_cfg1"]
+    which = sys.argv[1:] or ["video_tiny", "distilbert_tiny", "losses", "full_cfg1", "retrieval"]
     for w in which:
         globals()[w]()

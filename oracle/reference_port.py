@@ -231,6 +231,72 @@ def max_margin_ranking_loss(x, margin=0.2, fix_norm=True):
     return h.sum() / (2 * n * n)
 
 
+def adaptive_max_margin_ranking_loss(x, weight, margin=0.4, fix_norm=True):
+    """AdaptiveMaxMarginRankingLoss.forward (model/loss.py:100-133): anchor i's margin is weight[i] * margin in both
+    the row (x_ij) and the column (x_ji) terms."""
+    n = x.shape[0]
+    d = x.diagonal().unsqueeze(1)
+    m = weight.reshape(n, 1) * margin
+    h = torch.relu(m - (d - x)) + torch.relu(m - (d - x.t()))
+    if fix_norm:
+        off = 1.0 - torch.eye(n, dtype=x.dtype, device=x.device)
+        return (h * off).sum() / (2 * n * (n - 1))
+    return h.sum() / (2 * n * n)
+
+
+# ----------------------------------------------------------------------------------------------
+# EPIC-Kitchens MIR ranking metrics (numpy, float64 accumulation like the reference)
+# ----------------------------------------------------------------------------------------------
+
+def _rank_desc(sim, tie_hi):
+    """Column order of every row, best first.  tie_hi=True: stable ascending argsort reversed (utils/nDCG.py:32);
+    tie_hi=False: stable argsort of -sim (utils/mAP.py:25).  (The reference's default argsort kind is not stable;
+    on tie-free similarities all variants agree.)"""
+    import numpy as np
+    if tie_hi:
+        return np.argsort(sim, axis=1, kind="stable")[:, ::-1]
+    return np.argsort(-sim, axis=1, kind="stable")
+
+
+def k_counts_of(relevancy):
+    """utils/nDCG.py:47-75 calculate_k_counts: rank i counts iff i < #(relevancy[row] > 0)."""
+    import numpy as np
+    k = (relevancy > 0).sum(axis=1, keepdims=True)
+    return (np.arange(relevancy.shape[1])[None, :] < k).astype(int)
+
+
+def dcg(sim, relevancy, k_counts):
+    """utils/nDCG.py:3-45 calculate_DCG."""
+    import numpy as np
+    ranks = _rank_desc(np.asarray(sim), True)
+    rows = np.arange(sim.shape[0])[:, None]
+    num = np.asarray(relevancy, dtype=np.float64)[rows, ranks] * k_counts
+    return (num / np.log2(np.arange(sim.shape[1]) + 2.0)[None, :]).sum(axis=1)
+
+
+def ndcg(sim, relevancy, k_counts=None, idcg=None, reduction="mean"):
+    """utils/nDCG.py:96-139 calculate_nDCG (IDCG = DCG of the relevancy ranked by itself, :78-94)."""
+    import numpy as np
+    if k_counts is None:
+        k_counts = k_counts_of(relevancy)
+    d = dcg(sim, relevancy, k_counts)
+    if idcg is None:
+        idcg = dcg(relevancy, relevancy, k_counts)
+    return np.mean(d / idcg) if reduction == "mean" else d / idcg
+
+
+def average_precision(sim, relevancy):
+    """utils/mAP.py:4-44 calculate_mAP, per query (the reference returns the mean of this vector)."""
+    import numpy as np
+    order = _rank_desc(np.asarray(sim), False)
+    rows = np.arange(sim.shape[0])[:, None]
+    rel = np.asarray(relevancy, dtype=np.float64)[rows, order]
+    cum = np.cumsum(rel, axis=1)
+    cum[rel != 1] = 0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return (cum / (np.arange(rel.shape[1]) + 1.0)).sum(axis=1) / (rel == 1).sum(axis=1)
+
+
 def dual_softmax(sim):
     """run/test_epic.py:137-143: s = softmax(s/500, dim=1) * s ; s = softmax(s, dim=0)."""
     s = torch.softmax(sim / 500.0, dim=1) * sim

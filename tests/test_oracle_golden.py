@@ -88,3 +88,30 @@ def test_full_size_cfg1_forward_backward():
             got = p[k[2:]].grad.norm()
             assert abs(got.item() - ref.item()) <= 2e-3 * ref.item() + 1e-7, k  # k_lin.bias grads are analytically 0
     assert n >= 12
+
+
+def test_retrieval_oracle_vs_reference_golden():
+    """EPIC-MIR side: AdaptiveMaxMarginRankingLoss, utils/nDCG.py, utils/mAP.py (golden from the reference itself,
+    incl. its own known-answer example utils/nDCG.py:141-164)."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "retrieval.npz"))
+    x = torch.from_numpy(z["amm_x"]).requires_grad_(True)
+    w = torch.from_numpy(z["amm_w"])
+    l = rp.adaptive_max_margin_ranking_loss(x, w); l.backward()
+    close(l, torch.from_numpy(z["amm"])); close(x.grad, torch.from_numpy(z["amm_dx"]), atol=1e-7)
+    close(rp.adaptive_max_margin_ranking_loss(x.detach(), w, fix_norm=False), torch.from_numpy(z["amm_nofix"]))
+    sim, rel = z["rk_sim"], z["rk_rel"]
+    kc = rp.k_counts_of(rel)
+    assert np.array_equal(kc, z["rk_kcounts"])
+    np.testing.assert_allclose(rp.dcg(sim, rel, kc), z["rk_dcg"], rtol=1e-12)
+    np.testing.assert_allclose(rp.dcg(rel, rel, kc), z["rk_idcg"], rtol=1e-12)
+    np.testing.assert_allclose(rp.ndcg(sim, rel), z["rk_ndcg"], rtol=1e-12)
+    np.testing.assert_allclose(rp.ndcg(sim, rel, reduction=None), z["rk_ndcg_vec"], rtol=1e-12)
+    np.testing.assert_allclose(rp.average_precision(sim, rel).mean(), z["rk_map"], rtol=1e-12)
+    with np.errstate(invalid="ignore", divide="ignore"):        # gallery items without any relevant query: NaN, as numpy
+        np.testing.assert_allclose(rp.ndcg(sim.T, rel.T), z["rk_ndcg_t"], rtol=1e-12, equal_nan=True)
+        np.testing.assert_allclose(rp.average_precision(sim.T, rel.T).mean(), z["rk_map_t"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(rp.ndcg(z["ka_sim"], z["ka_rel"]), z["ka_ndcg"], rtol=1e-12)
+    np.testing.assert_allclose(rp.average_precision(z["ka_sim"], z["ka_rel"]).mean(), z["ka_map"], rtol=1e-12)
