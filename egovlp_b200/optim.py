@@ -23,7 +23,10 @@ class AdamW(torch.optim.Optimizer):
         self._tables = {}
 
     def _table(self, gi, plist):
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
+        # the device-side pointer table is rebuilt whenever a tensor moved (new .grad after zero_grad(set_to_none),
+        # optimizer state replaced by load_state_dict, ...)
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
+                     self.state[p]["exp_avg_sq"].data_ptr()) for p in plist)
         ent = self._tables.get(gi)
         if ent is not None and ent[0] == key:
             return ent[1:]
