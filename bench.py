@@ -293,6 +293,14 @@ def main():
         f_step, f_video, f_text = flops_per_clip(T, L)
         peak_tf = peaks["bf16_tflops_sustained"]
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        # DRAM bytes of the same launches from the committed ncu capture (valid for the default workload only)
+        traffic, traffic_src = None, None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemm_dram_traffic.json")
+        if os.path.exists(tpath) and (args.batch, T, L) == (64, 16, 16):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes_per_step"] / tj["launches_per_step"]
+            traffic_src = "profiles/r1_gemm_dram_traffic.json (ncu dram__bytes_read+write.sum, mean per GEMM launch of one step)"
         line = {"metric": "clips/sec, 16-frame TimeSformer-B + DistilBERT + EgoNCE training step",
                 "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -302,7 +310,9 @@ def main():
                 "gflop_per_clip_step": f_step / 1e9,
                 "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all fwd/dgrad/wgrad launches)",
                              "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                             "frac": achieved / peak_tf if achieved else None, "traffic": None,
+                             "frac": achieved / peak_tf if achieved else None, "traffic": traffic,
+                             "traffic_unit": "bytes per launch", "traffic_source": traffic_src,
+                             "algorithmic_flop_per_launch": gemm_flops / gemm_calls if gemm_calls else None,
                              "launches_per_step": gemm_calls / args.steps, "share_of_step": gemm_ms / ms_total,
                              "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
