@@ -304,7 +304,7 @@ def main():
         line = {"metric": "clips/sec, 16-frame TimeSformer-B + DistilBERT + EgoNCE training step",
                 "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16", "data": "synthetic (seeded video/text/tags, seeded random-init weights, no dropout)",
+                "dtype": "bf16", "data": "synthetic (seeded video/text/tags, seeded random-init weights; text-tower dropout 0.1 active as in the reference's train mode)",
                 "config": workload_config(args, world), "loss": loss_val,
                 "step_flop_fraction_of_peak": value / world * f_step / (peak_tf * 1e12),
                 "gflop_per_clip_step": f_step / 1e9,

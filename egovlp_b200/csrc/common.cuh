@@ -103,6 +103,31 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Counter-based RNG for dropout: Philox4x32-10 keyed by (seed, site), counter = element group.  Stateless, so the
+// backward regenerates the forward's mask from (seed, site, index) instead of storing it.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(unsigned long long key, unsigned long long ctr) {
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x2B7E1516u, c3 = 0x28AED2A6u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ unsigned long long dropout_key(unsigned long long seed, uint32_t site) {
+  return seed ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(site + 1));
+}
+// keep-threshold: an element is DROPPED iff its 32 random bits are < p * 2^32
+__device__ __forceinline__ uint32_t dropout_threshold(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+// ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -34,7 +34,8 @@ __global__ void text_embed_bwd_kernel(const long long* __restrict__ ids, const f
 template <bool BWD>
 __global__ void __launch_bounds__(256)
 text_attn_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mask, bf16* __restrict__ out,
-                 const bf16* __restrict__ dout, bf16* __restrict__ dqkv, int B, int L, int H, float q_scale) {
+                 const bf16* __restrict__ dout, bf16* __restrict__ dqkv, int B, int L, int H, float q_scale,
+                 float p_drop, unsigned long long seed, uint32_t site) {
   extern __shared__ float sm[];
   const int D = H * HD, b = blockIdx.x / H, h = blockIdx.x % H;
   const int LP = L + 1, RS = HD + 1;
@@ -44,6 +45,10 @@ text_attn_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mas
   float* dO = v + L * RS;           // bwd only
   float* P = BWD ? dO + L * RS : v + L * RS;   // [L][L+1]
   float* keyok = P + L * LP;        // [L]
+  uint32_t* keep = reinterpret_cast<uint32_t*>(keyok + L);   // [L][4] bit j of row i: probability (i, j) survives dropout
+  const float inv_keep = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  const uint32_t thresh = dropout_threshold(p_drop);
+  const unsigned long long dkey = dropout_key(seed, site);
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
     const int r = i / HD, d = i % HD;
@@ -76,13 +81,24 @@ text_attn_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mas
     sum = warp_sum(sum);
     const float inv = 1.f / sum;
     for (int j = lane; j < L; j += 32) P[i * LP + j] *= inv;
+    // attention dropout (HF DistilBERT: `weights = dropout(softmax(scores))`): one Philox draw per (b, h, i, j)
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      bool kp = true;
+      if (p_drop > 0.f && j < L)
+        kp = philox4x32_10(dkey, ((unsigned long long)blockIdx.x * L + i) * L + j).x >= thresh;
+      const uint32_t word = __ballot_sync(0xffffffffu, kp);
+      if (lane == 0) keep[i * 4 + jj] = word;
+    }
   }
   __syncthreads();
+#define DROPF(i, j) (((keep[(i) * 4 + ((j) >> 5)] >> ((j) & 31)) & 1u) ? inv_keep : 0.f)
   if (!BWD) {
     for (int i = warp; i < L; i += nw) {
       float o0 = 0.f, o1 = 0.f;
       for (int j = 0; j < L; ++j) {
-        const float p = P[i * LP + j];
+        const float p = P[i * LP + j] * DROPF(i, j);
         o0 += p * v[j * RS + lane];
         o1 += p * v[j * RS + lane + 32];
       }
@@ -97,7 +113,7 @@ text_attn_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mas
   for (int j = warp; j < L; j += nw) {
     float a0 = 0.f, a1 = 0.f;
     for (int i = 0; i < L; ++i) {
-      const float p = P[i * LP + j];
+      const float p = P[i * LP + j] * DROPF(i, j);
       a0 += p * dO[i * RS + lane];
       a1 += p * dO[i * RS + lane + 32];
     }
@@ -117,6 +133,7 @@ text_attn_kernel(const bf16* __restrict__ qkv, const long long* __restrict__ mas
       if (j < L) {
 #pragma unroll 16
         for (int d = 0; d < HD; ++d) dp += dO[i * RS + d] * v[j * RS + d];
+        dp *= DROPF(i, j);                       // d(dropped probs) -> d(softmax probs)
         delta += P[i * LP + j] * dp;
       }
       dp_local[jj] = dp;
@@ -172,7 +189,30 @@ __global__ void relu_rows_bwd_kernel(const float* __restrict__ x, long long row_
   dx[o] = x[o] > 0.f ? dh[i] : 0.f;
 }
 
-size_t text_attn_smem(int L, bool bwd) { return (size_t)((bwd ? 4 : 3) * L * (HD + 1) + L * (L + 1) + L) * sizeof(float); }
+size_t text_attn_smem(int L, bool bwd) {
+  return (size_t)((bwd ? 4 : 3) * L * (HD + 1) + L * (L + 1) + L + 4 * L) * sizeof(float);
+}
+
+// y = dropout(x) (+ add): fp32 and / or bf16 outputs; the same (seed, site) in the backward reproduces the mask
+__global__ void dropout_kernel(const float* __restrict__ x, const float* __restrict__ add, float* __restrict__ y32,
+                               bf16* __restrict__ y16, long long n4, float p, unsigned long long seed, uint32_t site) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n4) return;
+  const uint4 r = philox4x32_10(dropout_key(seed, site), (unsigned long long)g);
+  const uint32_t thresh = dropout_threshold(p);
+  const float inv = 1.f / (1.f - p);
+  float4 v = reinterpret_cast<const float4*>(x)[g];
+  v.x = r.x >= thresh ? v.x * inv : 0.f;
+  v.y = r.y >= thresh ? v.y * inv : 0.f;
+  v.z = r.z >= thresh ? v.z * inv : 0.f;
+  v.w = r.w >= thresh ? v.w * inv : 0.f;
+  if (add) {
+    const float4 a = reinterpret_cast<const float4*>(add)[g];
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+  }
+  if (y32) reinterpret_cast<float4*>(y32)[g] = v;
+  if (y16) reinterpret_cast<uint2*>(y16)[g] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
 
 }  // namespace
 }  // namespace egovlp
@@ -196,28 +236,41 @@ extern "C" int egovlp_text_embed_bwd(const long long* input_ids, const float* ds
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
+extern "C" int egovlp_dropout(const float* x, const float* add, float* y32, void* y16, long long n, float p,
+                              unsigned long long seed, unsigned int site, void* stream) {
+  EGOVLP_CHECK_ARG(x && (y32 || y16) && n >= 0 && n % 4 == 0, "dropout: bad args (n must be a multiple of 4)");
+  EGOVLP_CHECK_ARG(p >= 0.f && p < 1.f, "dropout: p=%f outside [0, 1)", p);
+  if (n == 0) return EGOVLP_OK;
+  dropout_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, ST(stream)>>>(x, add, y32, reinterpret_cast<bf16*>(y16), n / 4,
+                                                                          p, seed, site);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
 extern "C" int egovlp_text_attn_fwd(const void* qkv, const long long* attention_mask, void* out, int B, int L, int H,
-                                    void* stream) {
+                                    float p_drop, unsigned long long seed, unsigned int site, void* stream) {
   EGOVLP_CHECK_ARG(qkv && attention_mask && out && B > 0 && H > 0, "text_attn_fwd: bad args");
+  EGOVLP_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "text_attn: p_drop=%f outside [0, 1)", p_drop);
   EGOVLP_CHECK_ARG(L > 0 && L <= 128, "text_attn: L=%d unsupported (1..128)", L);
   const size_t smem = text_attn_smem(L, false);
   auto kern = text_attn_kernel<false>;
   EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<B * H, 256, smem, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), attention_mask,
-                                        reinterpret_cast<bf16*>(out), nullptr, nullptr, B, L, H, 1.f);
+                                        reinterpret_cast<bf16*>(out), nullptr, nullptr, B, L, H, 1.f, p_drop, seed, site);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }
 extern "C" int egovlp_text_attn_bwd(const void* qkv, const long long* attention_mask, const void* dout, void* dqkv,
-                                    int B, int L, int H, float q_scale, void* stream) {
+                                    int B, int L, int H, float q_scale, float p_drop, unsigned long long seed,
+                                    unsigned int site, void* stream) {
   EGOVLP_CHECK_ARG(qkv && attention_mask && dout && dqkv && B > 0 && H > 0, "text_attn_bwd: bad args");
+  EGOVLP_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "text_attn: p_drop=%f outside [0, 1)", p_drop);
   EGOVLP_CHECK_ARG(L > 0 && L <= 128, "text_attn: L=%d unsupported (1..128)", L);
   const size_t smem = text_attn_smem(L, true);
   auto kern = text_attn_kernel<true>;
   EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<B * H, 256, smem, ST(stream)>>>(reinterpret_cast<const bf16*>(qkv), attention_mask, nullptr,
                                         reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dqkv), B, L, H,
-                                        q_scale);
+                                        q_scale, p_drop, seed, site);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;
 }

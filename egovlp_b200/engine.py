@@ -292,10 +292,14 @@ class TextTowerFn(torch.autograd.Function):
     params: word_emb, pos_emb, emb_ln.{w,b}, then per layer
             q.{w,b}, k.{w,b}, v.{w,b}, out.{w,b}, sa_ln.{w,b}, lin1.{w,b}, lin2.{w,b}, out_ln.{w,b}   (16 / layer),
             finally txt_proj.{w,b}.
-    Dropout of the HF model is not applied (deterministic parity path)."""
+    `drop` = (p_hidden, p_attention): HuggingFace DistilBERT's train-mode dropouts -- on the embedding LayerNorm output,
+    on the attention probabilities and on the FFN output (modeling_distilbert.py; the reference calls
+    `self.text_model.train()`, model/model.py:36).  Masks come from a counter-based Philox stream keyed by one seed
+    drawn per forward from torch's CPU generator (so `torch.manual_seed` makes a run reproducible); the backward
+    regenerates them.  (0, 0) = eval mode / the deterministic parity path."""
 
     @staticmethod
-    def forward(ctx, input_ids, attention_mask, heads, eps, tokens_mode, cache, *p):
+    def forward(ctx, input_ids, attention_mask, heads, eps, tokens_mode, cache, drop, *p):
         word, pos, elw, elb = p[:4]
         pw, pb = p[-2:]
         layers = [p[4 + 16 * i: 4 + 16 * (i + 1)] for i in range((len(p) - 6) // 16)]
@@ -307,12 +311,16 @@ class TextTowerFn(torch.autograd.Function):
         dev = word
         train = any(ctx.needs_input_grad)
         saved = []
+        p_hid, p_att = (float(drop[0]), float(drop[1])) if drop else (0.0, 0.0)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (p_hid > 0 or p_att > 0) else 0
 
         emb = _empty((M, D), F32, dev)
         ops.text_embed_fwd(ids, word.detach(), pos.detach(), emb, B, L, D)
         x, x16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
         mean, rstd = _empty((M,), F32, dev), _empty((M,), F32, dev)
         ops.layernorm_fwd(emb, elw.detach(), elb.detach(), eps, y16=x16, y32=x, mean=mean, rstd=rstd)
+        if p_hid > 0:
+            ops.dropout(x, p_hid, seed, 0, y32=x, y16=x16)                                # embeddings dropout (in place)
         saved += [emb, mean, rstd]
         for li, lp in enumerate(layers):
             (qw, qb, kw, kb, vw, vb, ow, ob, sw, sb, l1w, l1b, l2w, l2b, fw, fb) = lp
@@ -322,7 +330,7 @@ class TextTowerFn(torch.autograd.Function):
             qkv = _empty((M, 3 * D), BF16, dev)
             ops.gemm(x16, wqkv, qkv, bias=bqkv, col_scale=Q_SCALE, col_scale_ncols=D)
             ctxv = _empty((M, D), BF16, dev)
-            ops.text_attn_fwd(qkv, mask, ctxv, B, L, heads)
+            ops.text_attn_fwd(qkv, mask, ctxv, B, L, heads, p_att, seed, 1 + 2 * li)
             sa = _empty((M, D), F32, dev)
             ops.gemm(ctxv, cache.get(ow), sa, bias=ob.detach(), residual=x)               # sa_output + x
             x1, x1_16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
@@ -331,7 +339,11 @@ class TextTowerFn(torch.autograd.Function):
             hh, u = _empty((M, HID), BF16, dev), (_empty((M, HID), BF16, dev) if train else None)
             ops.gemm(x1_16, cache.get(l1w), hh, bias=l1b.detach(), act=1, out2=u)
             ff = _empty((M, D), F32, dev)
-            ops.gemm(hh, cache.get(l2w), ff, bias=l2b.detach(), residual=x1)              # ffn_output + sa_output
+            if p_hid > 0:
+                ops.gemm(hh, cache.get(l2w), ff, bias=l2b.detach())
+                ops.dropout(ff, p_hid, seed, 2 + 2 * li, add=x1, y32=ff)                   # dropout(ffn_output) + sa_output
+            else:
+                ops.gemm(hh, cache.get(l2w), ff, bias=l2b.detach(), residual=x1)          # ffn_output + sa_output
             xn, xn16 = _empty((M, D), F32, dev), _empty((M, D), BF16, dev)
             m2, r2 = _empty((M,), F32, dev), _empty((M,), F32, dev)
             ops.layernorm_fwd(ff, fw.detach(), fb.detach(), eps, y16=xn16, y32=xn, mean=m2, rstd=r2)
@@ -343,14 +355,14 @@ class TextTowerFn(torch.autograd.Function):
         out = _empty((rows, pw.shape[0]), F32, dev)
         ops.gemm(r16, cache.get(pw), out, bias=pb.detach())
         if train:
-            ctx.meta = (B, L, D, heads, tokens_mode, len(layers), len(saved))
+            ctx.meta = (B, L, D, heads, tokens_mode, len(layers), len(saved), p_hid, p_att, seed)
             ctx.cache = cache
             ctx.save_for_backward(ids, mask, x, r16, *saved, *p)
         return out.view(B, L, -1) if tokens_mode else out
 
     @staticmethod
     def backward(ctx, dout):
-        B, L, D, heads, tokens_mode, n_layers, n_saved = ctx.meta
+        B, L, D, heads, tokens_mode, n_layers, n_saved, p_hid, p_att, seed = ctx.meta
         cache = ctx.cache
         sv = ctx.saved_tensors
         ids, mask, x_last, r16 = sv[:4]
@@ -377,9 +389,13 @@ class TextTowerFn(torch.autograd.Function):
             dff, dff16 = _empty((M, D), F32, dout), _empty((M, D), BF16, dout)
             g_fw, g_fb = _zeros((D,), dout), _zeros((D,), dout)
             ops.layernorm_bwd(dx, ff, fw.detach(), m2, r2, dx=dff, dx16=dff16, dgamma=g_fw, dbeta=g_fb)
-            g_l2w, g_l2b = wgrad(dff16, hh, D, HID), bgrad(dff)
+            dffn, dffn16 = dff, dff16                      # gradient of the FFN output (before its dropout)
+            if p_hid > 0:
+                dffn, dffn16 = _empty((M, D), F32, dout), _empty((M, D), BF16, dout)
+                ops.dropout(dff, p_hid, seed, 2 + 2 * li, y32=dffn, y16=dffn16)
+            g_l2w, g_l2b = wgrad(dffn16, hh, D, HID), bgrad(dffn)
             du = _empty((M, HID), BF16, dout)
-            ops.gemm(dff16, cache.get(l2w), du, b_mn=True, aux=u, act=2)
+            ops.gemm(dffn16, cache.get(l2w), du, b_mn=True, aux=u, act=2)
             g_l1w, g_l1b = wgrad(du, x1_16, HID, D), bgrad(du)
             dx1 = _empty((M, D), F32, dout)
             ops.gemm(du, cache.get(l1w), dx1, b_mn=True, residual=dff)                     # + residual path
@@ -390,7 +406,7 @@ class TextTowerFn(torch.autograd.Function):
             dctx = _empty((M, D), BF16, dout)
             ops.gemm(dsa16, cache.get(ow), dctx, b_mn=True)
             dqkv = _empty((M, 3 * D), BF16, dout)
-            ops.text_attn_bwd(qkv, mask, dctx, dqkv, B, L, heads, Q_SCALE)
+            ops.text_attn_bwd(qkv, mask, dctx, dqkv, B, L, heads, Q_SCALE, p_att, seed, 1 + 2 * li)
             g_wqkv, g_bqkv = wgrad(dqkv, x16, 3 * D, D), bgrad(dqkv)
             wqkv = cache.cat(("text_qkv_w", li, id(qw)), (qw, kw, vw))
             dxin = _empty((M, D), F32, dout)
@@ -400,12 +416,14 @@ class TextTowerFn(torch.autograd.Function):
             bq, bk, bv = g_bqkv[:D], g_bqkv[D:2 * D], g_bqkv[2 * D:]
             grads = [gq, bq, gk, bk, gv, bv, g_ow, g_ob, g_sw, g_sb, g_l1w, g_l1b, g_l2w, g_l2b, g_fw, g_fb] + grads
         emb, mean, rstd = saved[:3]
+        if p_hid > 0:
+            ops.dropout(dx, p_hid, seed, 0, y32=dx)                                       # embeddings dropout, backward
         demb = _empty((M, D), F32, dout)
         g_elw, g_elb = _zeros((D,), dout), _zeros((D,), dout)
         ops.layernorm_bwd(dx, emb, elw.detach(), mean, rstd, dx=demb, dgamma=g_elw, dbeta=g_elb)
         g_word, g_pos = torch.zeros_like(word), torch.zeros_like(pos)
         ops.text_embed_bwd(ids, demb, g_word, g_pos, B, L, D)
-        return (None, None, None, None, None, None, g_word, g_pos, g_elw, g_elb, *grads, g_pw, g_pb)
+        return (None, None, None, None, None, None, None, g_word, g_pos, g_elw, g_elb, *grads, g_pw, g_pb)
 
 
 # ----------------------------------------------------------------------------------------------------------

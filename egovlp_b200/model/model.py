@@ -137,8 +137,11 @@ class FrozenInTime(BaseModel):
             raise NotImplementedError("projection='' is not implemented for the text tower")
         proj = self.txt_proj[1]
         cfg = self.text_model.config
+        # train-mode dropouts of the HF text model (the reference keeps `text_model.train()`, :36); eval() or a config
+        # with dropout = attention_dropout = 0 gives the deterministic path
+        drop = (cfg.dropout, cfg.attention_dropout) if self.text_model.training else (0.0, 0.0)
         return engine.TextTowerFn.apply(text_data['input_ids'], text_data['attention_mask'], cfg.n_heads, 1e-12,
-                                        tokens_mode, self._bf16_cache, *self._text_params(), proj.weight, proj.bias)
+                                        tokens_mode, self._bf16_cache, drop, *self._text_params(), proj.weight, proj.bias)
 
     def compute_text(self, text_data):
         return self._text(text_data, False)

@@ -192,13 +192,24 @@ def text_embed_bwd(ids, dsum, dword, dpos, B, L, D):
     call("egovlp_text_embed_bwd", _ptr(ids), _ptr(dsum), _ptr(dword), _ptr(dpos), B, L, D, _stream())
 
 
-def text_attn_fwd(qkv, mask, out, B, L, H):
+def text_attn_fwd(qkv, mask, out, B, L, H, p_drop=0.0, seed=0, site=0):
     assert mask.dtype == torch.int64 and mask.is_contiguous()
-    call("egovlp_text_attn_fwd", _ptr(qkv), _ptr(mask), _ptr(out), B, L, H, _stream())
+    call("egovlp_text_attn_fwd", _ptr(qkv), _ptr(mask), _ptr(out), B, L, H, C.c_float(p_drop), C.c_ulonglong(seed),
+         C.c_uint(site), _stream())
 
 
-def text_attn_bwd(qkv, mask, dout, dqkv, B, L, H, q_scale):
-    call("egovlp_text_attn_bwd", _ptr(qkv), _ptr(mask), _ptr(dout), _ptr(dqkv), B, L, H, C.c_float(q_scale), _stream())
+def text_attn_bwd(qkv, mask, dout, dqkv, B, L, H, q_scale, p_drop=0.0, seed=0, site=0):
+    call("egovlp_text_attn_bwd", _ptr(qkv), _ptr(mask), _ptr(dout), _ptr(dqkv), B, L, H, C.c_float(q_scale),
+         C.c_float(p_drop), C.c_ulonglong(seed), C.c_uint(site), _stream())
+
+
+def dropout(x, p, seed, site, add=None, y32=None, y16=None):
+    """y = dropout_p(x) (+ add) with the (seed, site) Philox mask; returns (y32, y16) (whichever were given)."""
+    _chk(x, F32, "x")
+    assert x.is_contiguous() and (y32 is not None or y16 is not None)
+    call("egovlp_dropout", _ptr(x), _ptr(add), _ptr(y32), _ptr(y16), C.c_longlong(x.numel()), C.c_float(p),
+         C.c_ulonglong(seed), C.c_uint(site), _stream())
+    return y32, y16
 
 
 def relu_rows_fwd(x, row_stride, out, rows, D):

@@ -130,15 +130,25 @@ int egovlp_video_embed_bwd(const float* dx, float* tmp_SD, float* dcls, float* d
  *   text_attn_fwd  : out bf16 [B*L, D] = softmax(q k^T + key-padding mask) v per (b, head); qkv bf16 [B*L, 3D],
  *                    q pre-scaled by 64^-0.5
  *   text_attn_bwd  : dqkv bf16 [B*L, 3D]  (dq multiplied by q_scale)
+ *                    p_drop / seed / site: attention dropout on the probabilities as HuggingFace DistilBERT applies it
+ *                    in train mode (transformers modeling_distilbert.py, `weights = self.dropout(weights)`), mask
+ *                    drawn from a counter-based Philox4x32-10 keyed by (seed, site) and indexed by (b, head, i, j);
+ *                    the backward must be given the forward's (p_drop, seed, site).  p_drop = 0 disables it.
+ *   dropout        : y = dropout_p(x) (+ add), fp32 [n] -> fp32 y32 and / or bf16 y16 (n % 4 == 0).  The embedding and
+ *                    FFN-output dropouts of DistilBERT (reference model/model.py:36 puts the text model in train mode);
+ *                    calling it on a gradient with the same (p, seed, site) is the backward.
  *   relu_rows      : out bf16 [rows, D] = relu(x[r*row_stride + :D]) (CLS -> ReLU of txt_proj, model/model.py:73-75)
  */
 int egovlp_text_embed_fwd(const long long* input_ids, const float* word_emb, const float* pos_emb, float* out, int B,
                           int L, int D, void* stream);
 int egovlp_text_embed_bwd(const long long* input_ids, const float* dsum, float* dword, float* dpos, int B, int L, int D,
                           void* stream);
-int egovlp_text_attn_fwd(const void* qkv, const long long* attention_mask, void* out, int B, int L, int H, void* stream);
+int egovlp_text_attn_fwd(const void* qkv, const long long* attention_mask, void* out, int B, int L, int H, float p_drop,
+                         unsigned long long seed, unsigned int site, void* stream);
 int egovlp_text_attn_bwd(const void* qkv, const long long* attention_mask, const void* dout, void* dqkv, int B, int L,
-                         int H, float q_scale, void* stream);
+                         int H, float q_scale, float p_drop, unsigned long long seed, unsigned int site, void* stream);
+int egovlp_dropout(const float* x, const float* add, float* y32, void* y16_bf16, long long n, float p,
+                   unsigned long long seed, unsigned int site, void* stream);
 int egovlp_relu_rows_fwd(const float* x, long long row_stride, void* out_bf16, int rows, int D, void* stream);
 int egovlp_relu_rows_bwd(const float* x, long long row_stride, const float* dh, float* dx, int rows, int D, void* stream);
 

@@ -124,8 +124,11 @@ def video_tower(video, p, heads=12, prefix="video_model.", eps=1e-6):
 # text tower  (transformers DistilBertModel; call sites model/model.py:32-36,119-122)
 # ----------------------------------------------------------------------------------------------
 
-def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_model.", eps=1e-12):
-    """DistilBERT encoder, dropout disabled: returns last_hidden_state [B, L, D]."""
+def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_model.", eps=1e-12, dropout=None):
+    """DistilBERT encoder: returns last_hidden_state [B, L, D].  `dropout` = None (eval / p = 0) or a dict of
+    MULTIPLIERS (mask / (1 - p)) for HF's three train-mode dropout sites (modeling_distilbert.py): "emb" [B, L, D] on the
+    embedding LayerNorm output, ("att", layer) [B, H, L, L] on the attention probabilities, ("ffn", layer) [B, L, D] on
+    the FFN output -- the masks themselves are the RNG's business, the arithmetic around them is the oracle's."""
     B, L = input_ids.shape
     we = p[prefix + "embeddings.word_embeddings.weight"]
     pe = p[prefix + "embeddings.position_embeddings.weight"]
@@ -133,6 +136,8 @@ def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_mode
     d = D // heads
     x = we[input_ids] + pe[:L].unsqueeze(0)
     x = F.layer_norm(x, (D,), p[prefix + "embeddings.LayerNorm.weight"], p[prefix + "embeddings.LayerNorm.bias"], eps)
+    if dropout is not None:
+        x = x * dropout["emb"]
     key_bias = torch.zeros(B, 1, 1, L, dtype=x.dtype, device=x.device)
     key_bias = key_bias.masked_fill(attention_mask.reshape(B, 1, 1, L) == 0, float("-inf"))
     n_layers = 1 + max(int(k.split("transformer.layer.")[1].split(".")[0]) for k in p if "transformer.layer." in k)
@@ -146,11 +151,15 @@ def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_mode
         k = heads_of(_linear(x, p[lp + "attention.k_lin.weight"], p[lp + "attention.k_lin.bias"]))
         v = heads_of(_linear(x, p[lp + "attention.v_lin.weight"], p[lp + "attention.v_lin.bias"]))
         w = torch.softmax(q @ k.transpose(-1, -2) + key_bias, dim=-1)
+        if dropout is not None:
+            w = w * dropout[("att", i)]
         ctx = (w @ v).transpose(1, 2).reshape(B, L, D)
         sa = _linear(ctx, p[lp + "attention.out_lin.weight"], p[lp + "attention.out_lin.bias"])
         x = F.layer_norm(sa + x, (D,), p[lp + "sa_layer_norm.weight"], p[lp + "sa_layer_norm.bias"], eps)
         h = F.gelu(_linear(x, p[lp + "ffn.lin1.weight"], p[lp + "ffn.lin1.bias"]))
         h = _linear(h, p[lp + "ffn.lin2.weight"], p[lp + "ffn.lin2.bias"])
+        if dropout is not None:
+            h = h * dropout[("ffn", i)]
         x = F.layer_norm(h + x, (D,), p[lp + "output_layer_norm.weight"], p[lp + "output_layer_norm.bias"], eps)
     return x
 
@@ -159,15 +168,15 @@ def distilbert_forward(input_ids, attention_mask, p, heads=12, prefix="text_mode
 # dual encoder  (model/model.py)
 # ----------------------------------------------------------------------------------------------
 
-def compute_text(text, p, heads=12):
+def compute_text(text, p, heads=12, dropout=None):
     """FrozenInTime.compute_text (model/model.py:117-126): CLS -> ReLU -> Linear."""
-    h = distilbert_forward(text["input_ids"], text["attention_mask"], p, heads)[:, 0]
+    h = distilbert_forward(text["input_ids"], text["attention_mask"], p, heads, dropout=dropout)[:, 0]
     return _linear(torch.relu(h), p["txt_proj.1.weight"], p["txt_proj.1.bias"])
 
 
-def compute_text_tokens(text, p, heads=12):
+def compute_text_tokens(text, p, heads=12, dropout=None):
     """FrozenInTime.compute_text_tokens (model/model.py:128-138)."""
-    h = distilbert_forward(text["input_ids"], text["attention_mask"], p, heads)
+    h = distilbert_forward(text["input_ids"], text["attention_mask"], p, heads, dropout=dropout)
     return _linear(torch.relu(h), p["txt_proj.1.weight"], p["txt_proj.1.bias"])
 
 
