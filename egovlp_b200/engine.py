@@ -52,17 +52,29 @@ class Bf16Cache:
         self._store.clear()
 
 
-# bf16 twins of fp32 gradient tensors handed between consecutive Functions (saves one cast pass per block)
+# By-products of an fp32 gradient tensor handed between consecutive Functions: its bf16 twin (saves one cast pass per
+# block) and its column sums (the next block's fc2 bias gradient; saves one read of the tensor per block).  Keyed by
+# the tensor's storage + shape and consumed once, so a gradient that autograd re-materialised is simply recomputed.
 _twin = {}
 
 
-def _publish_twin(t32, t16):
+def _publish_twin(t32, t16, colsum=None):
     _twin.clear()
-    _twin[(t32.data_ptr(), tuple(t32.shape))] = t16
+    _twin[(t32.data_ptr(), tuple(t32.shape))] = (t16, colsum)
+
+
+def _byproducts_of(t32):
+    """-> (bf16 twin, column sums [D]) of an fp32 [M, D] gradient, from the producer if it published them."""
+    t16, colsum = _twin.pop((t32.data_ptr(), tuple(t32.shape)), (None, None))
+    if t16 is None:
+        t16 = ops.cast_bf16(t32.contiguous())
+    if colsum is None:
+        colsum = bgrad(t32)
+    return t16, colsum
 
 
 def _bf16_of(t32):
-    t16 = _twin.pop((t32.data_ptr(), tuple(t32.shape)), None)
+    t16, _ = _twin.pop((t32.data_ptr(), tuple(t32.shape)), (None, None))
     if t16 is None:
         t16 = ops.cast_bf16(t32.contiguous())
     return t16
@@ -189,10 +201,10 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         D = H * 64
         M = x2.shape[0]
         dy = dy.contiguous().view(M, D)
-        dy16 = _bf16_of(dy)
+        dy16, g_f2b = _byproducts_of(dy)                     # fc2 bias gradient = colsum(dy)
 
         # ---- MLP:  y = sr + fc2(gelu(fc1(LN2(sr))))
-        g_f2w, g_f2b = wgrad(dy16, h, D, HID), bgrad(dy)
+        g_f2w = wgrad(dy16, h, D, HID)
         du = _empty((M, HID), BF16, dy)
         g_f1b = _zeros((HID,), dy)
         ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=2, colsum=g_f1b)  # (dy W2) * gelu'(u); + bias grad
@@ -230,9 +242,10 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         g_tqw, g_tqb, g_tpw, dn3 = attention_bwd(dtr16, qkv_t, a_t, lse_t, n3, tqw, tpw, 0)
         dx, dx16 = _empty((M, D), F32, dy), _empty((M, D), BF16, dy)
         g_n3w, g_n3b = _zeros((D,), dy), _zeros((D,), dy)
+        dx_colsum = _zeros((D,), dy)                         # = the fc2 bias gradient of the block below
         ops.layernorm_bwd(dn3, x2, n3w.detach(), mean3, rstd3, add1=dsr16, add2=dtr16, dx=dx, dx16=dx16, dgamma=g_n3w,
-                          dbeta=g_n3b)
-        _publish_twin(dx, dx16)
+                          dbeta=g_n3b, colsum_dx=dx_colsum)
+        _publish_twin(dx, dx16, dx_colsum)
         S = 1 + T * N
         return (dx.view(B, S, D), None, None, None, g_n1w, g_n1b, g_sqw, g_sqb, g_spw, g_spb, g_tqw, g_tqb, g_tpw,
                 g_tpb, g_n2w, g_n2b, g_f1w, g_f1b, g_f2w, g_f2b, g_n3w, g_n3b)
