@@ -162,7 +162,7 @@ __device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int&
 }
 
 // Shared prologue: carve smem, gather the group's tiles (TMA) + CLS rows (manual), build the gid table.
-template <bool BWD, bool STAGE = !BWD>
+template <bool BWD, bool STAGE = !BWD, bool WAIT = true>
 __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_qkv, const CUtensorMap* tm_do,
                                            const bf16* qkv, const bf16* dout, int b, int h, int g, uint8_t* smem_gen,
                                            uint32_t smem_base, Smem& sm, int nwarps) {
@@ -217,7 +217,7 @@ __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_
     sm.gid[r] = gid;
   }
   __syncthreads();
-  mbar_wait(sm.bar, 0);
+  if (WAIT) mbar_wait(sm.bar, 0);     // !WAIT: the caller overlaps its own global loads with the TMA flight time
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -990,7 +990,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   int b, h, g;
   decode_block(G, b, h, g);
   Smem sm;
-  load_group<true>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  load_group<true, false, false>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -999,12 +999,33 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   c.valid_keys = TIME ? min(G.PG, G.N - g * G.PG) * G.T : G.NP;
   const FragOff fo = make_frag_off(lane);
 
-  // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row
-  for (int r = warp * 4 + (lane >> 3); r < G.NPAD; r += NWARPS * 4) {
+  // phase 0: lse (log2 units) and delta = rowsum(dO * O) per row.  The rows of O and the lse values come straight
+  // from global memory: their loads are issued BEFORE waiting for the TMA tiles so that both latencies overlap.
+  constexpr int P0_ROWS = NWARPS * 4;                      // rows per pass (8 lanes x 16 B per row)
+  constexpr int P0_MAX = (256 + P0_ROWS - 1) / P0_ROWS;    // NPAD <= 256
+  uint4 o_pre[TIME ? 128 / P0_ROWS : P0_MAX];
+  float l_pre[TIME ? 128 / P0_ROWS : P0_MAX];
+  constexpr int P0_N = TIME ? 128 / P0_ROWS : P0_MAX;
+#pragma unroll
+  for (int i = 0; i < P0_N; ++i) {
+    const int r = warp * 4 + (lane >> 3) + i * P0_ROWS;
+    const int tok = r < G.NPAD ? row_token(G, g, r) : -1;
+    o_pre[i] = make_uint4(0, 0, 0, 0);
+    l_pre[i] = 0.f;
+    if (tok >= 0) {
+      o_pre[i] = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + (lane & 7) * 8);
+      l_pre[i] = lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E;
+    }
+  }
+  mbar_wait(sm.bar, 0);
+#pragma unroll
+  for (int i = 0; i < P0_N; ++i) {
+    const int r = warp * 4 + (lane >> 3) + i * P0_ROWS;
+    if (r >= G.NPAD) break;
     const int tok = row_token(G, g, r), cc = lane & 7;
     float d = 0.f;
     if (tok >= 0) {
-      const uint4 ov = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + cc * 8);
+      const uint4 ov = o_pre[i];
       const uint4 dv = *reinterpret_cast<const uint4*>(smem_gen + (sw_addr(sm.dout, r, cc) - smem_base));
       const uint32_t ou[4] = {ov.x, ov.y, ov.z, ov.w}, du[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
@@ -1016,7 +1037,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
     if (cc == 0) {
       sm.delta[r] = d;
-      sm.lse[r] = tok >= 0 ? lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E : 0.f;
+      sm.lse[r] = l_pre[i];
     }
   }
   __syncthreads();

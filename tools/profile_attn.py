@@ -1,7 +1,7 @@
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from egovlp_b200 import ops
-B, T, N, H = 8, 16, 196, 12
+B, T, N, H = int(os.environ.get("B", 8)), 16, 196, 12
 S, D = 1 + T * N, 64 * H
 M = B * S
 qkv = torch.randn(M, 3 * D, device="cuda").bfloat16(); qkv[:, :D] *= 0.125
