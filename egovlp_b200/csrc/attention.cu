@@ -80,6 +80,17 @@ __device__ __forceinline__ int row_token(const Geom& G, int g, int r) {
   return n < G.N ? 1 + f * G.N + n : -1;
 }
 
+// The same for the specialised kernels, without the integer division: RT = 1 space, RT = 2 time with T = 1 << sh.
+template <int RT>
+__device__ __forceinline__ int row_token_x(const Geom& G, int g, int r, int sh) {
+  if (RT == 0) return row_token(G, g, r);
+  if (r == G.NP) return 0;
+  if (r > G.NP) return -1;
+  if (RT == 1) return 1 + g * G.N + r;
+  const int n = g * G.PG + (r >> sh);
+  return n < G.N ? 1 + (r & ((1 << sh) - 1)) * G.N + n : -1;
+}
+
 struct Smem {
   uint32_t q, k, v, dout;  // tile base addresses (shared space)
   short* gid;              // [NPAD] group id per row; -2 = CLS, -1 = invalid
@@ -108,9 +119,10 @@ __device__ __forceinline__ bool span_active(const Geom& G, int lo, int hi, int c
 
 // Stage a 16 x 64 fp32 fragment tile (mma C layout, 8 n-tiles) as bf16 into the warp's staging rows, then write
 // each valid row as one 128-byte line to dst[(b*S + token) * ld + col0 ...].
+template <int RT = 0>
 __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float s0, float s1, uint32_t stage,
                                                 uint8_t* stage_gen, bf16* dst, long long ld, int col0, const Geom& G,
-                                                int b, int g, int r0, int lane, bool skip_cls) {
+                                                int b, int g, int r0, int lane, bool skip_cls, int sh = 0) {
   const int gq = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -122,7 +134,7 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
 #pragma unroll
   for (int p = 0; p < 4; ++p) {
     const int rr = p * 4 + (lane >> 3), c = lane & 7;
-    const int tok = row_token(G, g, r0 + rr);
+    const int tok = row_token_x<RT>(G, g, r0 + rr, sh);
     if (tok > 0 || (tok == 0 && !skip_cls)) {
       const uint4 v = *reinterpret_cast<const uint4*>(stage_gen + (sw_addr(stage, rr, c) - stage));
       *reinterpret_cast<uint4*>(dst + ((long long)b * G.S + tok) * ld + col0 + c * 8) = v;
@@ -133,11 +145,13 @@ __device__ __forceinline__ void store_rows_bf16(const float (&acc)[8][4], float 
 
 // Same, straight from the fragments (each quad writes 16 contiguous bytes of a row): used by the backward, whose
 // four resident tiles leave no room for staging when two CTAs share an SM.
+template <int RT = 0>
 __device__ __forceinline__ void store_frag_rows_bf16(const float (&acc)[8][4], float s, bf16* dst, long long ld, int col0,
-                                                     const Geom& G, int b, int g, int r0, int lane, float s_hi = -1.f) {
+                                                     const Geom& G, int b, int g, int r0, int lane, float s_hi = -1.f,
+                                                     int sh = 0) {
   const float sB = s_hi >= 0.f ? s_hi : s;   // optional separate scale for the rows g+8
   const int gq = lane >> 2, t = lane & 3;
-  const int tok0 = row_token(G, g, r0 + gq), tok1 = row_token(G, g, r0 + gq + 8);
+  const int tok0 = row_token_x<RT>(G, g, r0 + gq, sh), tok1 = row_token_x<RT>(G, g, r0 + gq + 8, sh);
   bf16* p0 = dst + ((long long)b * G.S + tok0) * ld + col0 + 2 * t;
   bf16* p1 = dst + ((long long)b * G.S + tok1) * ld + col0 + 2 * t;
 #pragma unroll
@@ -162,7 +176,7 @@ __device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int&
 }
 
 // Shared prologue: carve smem, gather the group's tiles (TMA) + CLS rows (manual), build the gid table.
-template <bool BWD, bool STAGE = !BWD, bool WAIT = true>
+template <bool BWD, bool STAGE = !BWD, bool WAIT = true, bool GID = true>
 __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_qkv, const CUtensorMap* tm_do,
                                            const bf16* qkv, const bf16* dout, int b, int h, int g, uint8_t* smem_gen,
                                            uint32_t smem_base, Smem& sm, int nwarps) {
@@ -200,21 +214,26 @@ __device__ __forceinline__ void load_group(const Geom& G, const CUtensorMap* tm_
   }
   // CLS rows (row NP) + zero padding rows NP+1 .. NPAD-1, 16B chunks
   const int pad_rows = G.NPAD - G.NP;   // >= 1
-  for (int i = tid; i < ntiles * pad_rows * 8; i += blockDim.x) {
-    const int c = i & 7, rr = (i >> 3) % pad_rows, which = (i >> 3) / pad_rows;
-    uint4 val = make_uint4(0, 0, 0, 0);
-    if (rr == 0) {
-      const bf16* src = (which < 3) ? qkv + (long long)b * G.S * 3 * G.D + which * G.D + h * HD
-                                    : dout + (long long)b * G.S * G.D + h * HD;
-      val = *reinterpret_cast<const uint4*>(src + c * 8);
+  for (int i = tid; i < pad_rows * 8; i += blockDim.x) {
+    const int c = i & 7, rr = i >> 3;
+#pragma unroll
+    for (int which = 0; which < ntiles; ++which) {
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (rr == 0) {
+        const bf16* src = (which < 3) ? qkv + (long long)b * G.S * 3 * G.D + which * G.D + h * HD
+                                      : dout + (long long)b * G.S * G.D + h * HD;
+        val = *reinterpret_cast<const uint4*>(src + c * 8);
+      }
+      *reinterpret_cast<uint4*>(smem_gen + (sw_addr(sm.q + which * tile_bytes, G.NP + rr, c) - smem_base)) = val;
     }
-    *reinterpret_cast<uint4*>(smem_gen + (sw_addr(sm.q + which * tile_bytes, G.NP + rr, c) - smem_base)) = val;
   }
-  for (int r = tid; r < G.NPAD; r += blockDim.x) {
-    short gid = -1;
-    if (r == G.NP) gid = -2;
-    else if (r < G.NP && row_token(G, g, r) > 0) gid = (short)(r / G.gsize);
-    sm.gid[r] = gid;
+  if (GID) {                            // group-id table: only the generic kernels look rows up in it
+    for (int r = tid; r < G.NPAD; r += blockDim.x) {
+      short gid = -1;
+      if (r == G.NP) gid = -2;
+      else if (r < G.NP && row_token(G, g, r) > 0) gid = (short)(r / G.gsize);
+      sm.gid[r] = gid;
+    }
   }
   __syncthreads();
   if (WAIT) mbar_wait(sm.bar, 0);     // !WAIT: the caller overlaps its own global loads with the TMA flight time
@@ -718,10 +737,16 @@ __device__ __forceinline__ void fwd_chunk(const FastCtx& c, const Smem& sm, cons
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;
-          s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
-          s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
-          s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
-          s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
+          if (TIME && ch.base[p] == c.NP && rowA < c.NP) {    // patch rows x the CLS pair: only column NP is a key
+            const bool kc = jj == 0 && t == 0;
+            s[j][0] = kc ? s[j][0] : -INFINITY; s[j][1] = -INFINITY;
+            s[j][2] = kc ? s[j][2] : -INFINITY; s[j][3] = -INFINITY;
+          } else {
+            s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
+            s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
+            s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
+            s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
+          }
         }
       }
     }
@@ -787,7 +812,8 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
   int b, h, g;
   decode_block(G, b, h, g);
   Smem sm;
-  load_group<false, !TIME>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  load_group<false, !TIME, true, false>(G, &tm_qkv, nullptr, qkv, nullptr, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  constexpr int RT = TIME ? 2 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -838,12 +864,12 @@ fast_attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const bf16* __r
     if (part >= 0) continue;     // a CLS part: nothing else to store
     const float i0 = l0 > 0.f ? 1.f / l0 : 0.f, i1 = l1 > 0.f ? 1.f / l1 : 0.f;
     if (t == 0) {
-      const int tok0 = row_token(G, g, rowA), tok1 = row_token(G, g, rowB);
+      const int tok0 = row_token_x<RT>(G, g, rowA, sh), tok1 = row_token_x<RT>(G, g, rowB, sh);
       if (tok0 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok0] = m0 + logf(l0);
       if (tok1 > 0) lse_out[((long long)(b * G.H + h)) * G.S + tok1] = m1 + logf(l1);
     }
-    if (TIME) store_frag_rows_bf16(o, i0, out, G.D, h * HD, G, b, g, r0, lane, i1);   // no staging: 4 CTAs / SM
-    else store_rows_bf16(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true);
+    if (TIME) store_frag_rows_bf16<RT>(o, i0, out, G.D, h * HD, G, b, g, r0, lane, i1, sh);   // no staging: 4 CTAs / SM
+    else store_rows_bf16<RT>(o, i0, i1, stage, stage_gen, out, G.D, h * HD, G, b, g, r0, lane, /*skip_cls=*/true, sh);
   }
 }
 
@@ -881,10 +907,16 @@ __device__ __forceinline__ void bwd_q_chunk(const FastCtx& c, const Smem& sm, co
     for (int jj = 0; jj < 2; ++jj) {
       const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;
       if (masked) {               // exp2(-inf) = 0: masked entries drop out of P and dS
-        s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
-        s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
-        s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
-        s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
+        if (TIME && ch.base[p] == c.NP && r0 < c.NP) {        // patch rows x the CLS pair: only column NP is a key
+          const bool kc = jj == 0 && t == 0;
+          s[j][0] = kc ? s[j][0] : -INFINITY; s[j][1] = -INFINITY;
+          s[j][2] = kc ? s[j][2] : -INFINITY; s[j][3] = -INFINITY;
+        } else {
+          s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
+          s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
+          s[j][2] = fast_valid<TIME>(c, rowB, col) ? s[j][2] : -INFINITY;
+          s[j][3] = fast_valid<TIME>(c, rowB, col + 1) ? s[j][3] : -INFINITY;
+        }
       }
       float e0, e1, e2, e3;
       up2(fma2(pk2(s[j][0], s[j][1]), sc, nl0), e0, e1);
@@ -941,10 +973,16 @@ __device__ __forceinline__ void bwd_k_chunk(const FastCtx& c, const Smem& sm, co
     for (int jj = 0; jj < 2; ++jj) {
       const int j = 2 * p + jj, col = ch.base[p] + 8 * jj + 2 * t;       // query index
       if (masked) {
-        st[j][0] = fast_valid<TIME>(c, col, keyA) ? st[j][0] : -INFINITY;
-        st[j][1] = fast_valid<TIME>(c, col + 1, keyA) ? st[j][1] : -INFINITY;
-        st[j][2] = fast_valid<TIME>(c, col, keyB) ? st[j][2] : -INFINITY;
-        st[j][3] = fast_valid<TIME>(c, col + 1, keyB) ? st[j][3] : -INFINITY;
+        if (TIME && ch.base[p] == c.NP && k0r < c.NP) {       // patch keys x the CLS pair: only the CLS query (column NP)
+          const bool qc = jj == 0 && t == 0;
+          st[j][0] = (qc && keyA < c.valid_keys) ? st[j][0] : -INFINITY; st[j][1] = -INFINITY;
+          st[j][2] = (qc && keyB < c.valid_keys) ? st[j][2] : -INFINITY; st[j][3] = -INFINITY;
+        } else {
+          st[j][0] = fast_valid<TIME>(c, col, keyA) ? st[j][0] : -INFINITY;
+          st[j][1] = fast_valid<TIME>(c, col + 1, keyA) ? st[j][1] : -INFINITY;
+          st[j][2] = fast_valid<TIME>(c, col, keyB) ? st[j][2] : -INFINITY;
+          st[j][3] = fast_valid<TIME>(c, col + 1, keyB) ? st[j][3] : -INFINITY;
+        }
       }
       const float2 lq = *reinterpret_cast<const float2*>(sm.lse + col);
       const float2 dq2 = *reinterpret_cast<const float2*>(sm.delta + col);
@@ -990,7 +1028,8 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   int b, h, g;
   decode_block(G, b, h, g);
   Smem sm;
-  load_group<true, false, false>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  load_group<true, false, false, false>(G, &tm_qkv, &tm_do, qkv, dout, b, h, g, smem_gen, smem_base, sm, NWARPS);
+  constexpr int RT = TIME ? 2 : 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -1003,13 +1042,15 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   // from global memory: their loads are issued BEFORE waiting for the TMA tiles so that both latencies overlap.
   constexpr int P0_ROWS = NWARPS * 4;                      // rows per pass (8 lanes x 16 B per row)
   constexpr int P0_MAX = (256 + P0_ROWS - 1) / P0_ROWS;    // NPAD <= 256
-  uint4 o_pre[TIME ? 128 / P0_ROWS : P0_MAX];
-  float l_pre[TIME ? 128 / P0_ROWS : P0_MAX];
   constexpr int P0_N = TIME ? 128 / P0_ROWS : P0_MAX;
+  uint4 o_pre[P0_N];
+  float l_pre[P0_N];
+  int t_pre[P0_N];
 #pragma unroll
   for (int i = 0; i < P0_N; ++i) {
     const int r = warp * 4 + (lane >> 3) + i * P0_ROWS;
-    const int tok = r < G.NPAD ? row_token(G, g, r) : -1;
+    const int tok = r < G.NPAD ? row_token_x<RT>(G, g, r, sh) : -1;
+    t_pre[i] = tok;
     o_pre[i] = make_uint4(0, 0, 0, 0);
     l_pre[i] = 0.f;
     if (tok >= 0) {
@@ -1022,7 +1063,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
   for (int i = 0; i < P0_N; ++i) {
     const int r = warp * 4 + (lane >> 3) + i * P0_ROWS;
     if (r >= G.NPAD) break;
-    const int tok = row_token(G, g, r), cc = lane & 7;
+    const int tok = t_pre[i], cc = lane & 7;
     float d = 0.f;
     if (tok >= 0) {
       const uint4 ov = o_pre[i];
@@ -1069,7 +1110,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
         }
       }
     }
-    if (part < 0) store_frag_rows_bf16(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane);
+    if (part < 0) store_frag_rows_bf16<RT>(dq, q_scale, dqkv, 3 * G.D, h * HD, G, b, g, r0, lane, -1.f, sh);
   }
 
   // phase 2: per 16 keys -> dK, dV   (tile rows = keys, pairs = queries)
@@ -1102,8 +1143,8 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
       }
     }
     if (part < 0) {
-      store_frag_rows_bf16(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane);
-      store_frag_rows_bf16(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane);
+      store_frag_rows_bf16<RT>(dk, 1.f, dqkv, 3 * G.D, G.D + h * HD, G, b, g, k0r, lane, -1.f, sh);
+      store_frag_rows_bf16<RT>(dv, 1.f, dqkv, 3 * G.D, 2 * G.D + h * HD, G, b, g, k0r, lane, -1.f, sh);
     }
   }
 }
