@@ -168,11 +168,14 @@ __device__ __forceinline__ int tile_uniform_gid(const short* gid, int r0) {
   return (a >= 0 && a == b) ? a : -1;
 }
 
+// Head index fastest: the H CTAs launched back to back read the H adjacent 128-byte head slices of the SAME token
+// rows (q/k/v of one token are 3 x H x 128 B contiguous), so the scattered row reads of a group land in DRAM pages
+// that are already open instead of each 128-byte granule paying its own activation.
 __device__ __forceinline__ void decode_block(const Geom& G, int& b, int& h, int& g) {
-  g = blockIdx.x % G.G;
-  const int bh = blockIdx.x / G.G;
-  h = bh % G.H;
-  b = bh / G.H;
+  h = blockIdx.x % G.H;
+  const int bg = blockIdx.x / G.H;
+  g = bg % G.G;
+  b = bg / G.G;
 }
 
 // Shared prologue: carve smem, gather the group's tiles (TMA) + CLS rows (manual), build the gid table.
@@ -693,7 +696,8 @@ __device__ __forceinline__ bool get_chunk(const FastCtx& c, int T, int r0, int p
       ch.np = 2; ch.base[0] = r0; ch.base[1] = c.NP; ch.mask = (T < 16 ? 1u : 0u) | 2u;
       return true;
     }
-    const int w = c.NPAD / NWARPS;  // CLS part: w (= 32) consecutive rows
+    const int w = c.NPAD / NWARPS;  // CLS part: w (= 32 or 16) consecutive rows
+    if (CW >= 2 && NWARPS > 4) { ch.np = 1; ch.base[0] = part * w; ch.mask = 1u; return true; }
     if (CW >= 2) { ch.np = 2; ch.base[0] = part * w; ch.base[1] = part * w + 16; ch.mask = 3u; return true; }
     if (ci >= 2) return false;
     ch.np = 1; ch.base[0] = part * w + 16 * ci; ch.mask = 1u;
@@ -741,6 +745,11 @@ __device__ __forceinline__ void fwd_chunk(const FastCtx& c, const Smem& sm, cons
             const bool kc = jj == 0 && t == 0;
             s[j][0] = kc ? s[j][0] : -INFINITY; s[j][1] = -INFINITY;
             s[j][2] = kc ? s[j][2] : -INFINITY; s[j][3] = -INFINITY;
+          } else if (TIME && rowA >= c.NP && ch.base[p] < c.NP) {   // CLS tile x patch keys: row NP sees the valid keys
+            const bool cq = rowA == c.NP;
+            s[j][0] = (cq && col < c.valid_keys) ? s[j][0] : -INFINITY;
+            s[j][1] = (cq && col + 1 < c.valid_keys) ? s[j][1] : -INFINITY;
+            s[j][2] = -INFINITY; s[j][3] = -INFINITY;
           } else {
             s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
             s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
@@ -911,6 +920,11 @@ __device__ __forceinline__ void bwd_q_chunk(const FastCtx& c, const Smem& sm, co
           const bool kc = jj == 0 && t == 0;
           s[j][0] = kc ? s[j][0] : -INFINITY; s[j][1] = -INFINITY;
           s[j][2] = kc ? s[j][2] : -INFINITY; s[j][3] = -INFINITY;
+        } else if (TIME && r0 >= c.NP && ch.base[p] < c.NP) {   // CLS tile x patch keys: row NP sees the valid keys
+          const bool cq = rowA == c.NP;
+          s[j][0] = (cq && col < c.valid_keys) ? s[j][0] : -INFINITY;
+          s[j][1] = (cq && col + 1 < c.valid_keys) ? s[j][1] : -INFINITY;
+          s[j][2] = -INFINITY; s[j][3] = -INFINITY;
         } else {
           s[j][0] = fast_valid<TIME>(c, rowA, col) ? s[j][0] : -INFINITY;
           s[j][1] = fast_valid<TIME>(c, rowA, col + 1) ? s[j][1] : -INFINITY;
@@ -977,6 +991,10 @@ __device__ __forceinline__ void bwd_k_chunk(const FastCtx& c, const Smem& sm, co
           const bool qc = jj == 0 && t == 0;
           st[j][0] = (qc && keyA < c.valid_keys) ? st[j][0] : -INFINITY; st[j][1] = -INFINITY;
           st[j][2] = (qc && keyB < c.valid_keys) ? st[j][2] : -INFINITY; st[j][3] = -INFINITY;
+        } else if (TIME && k0r >= c.NP && ch.base[p] < c.NP) {   // CLS key tile x patch queries: every patch row sees key NP
+          const bool ck = keyA == c.NP;
+          st[j][0] = ck ? st[j][0] : -INFINITY; st[j][1] = ck ? st[j][1] : -INFINITY;
+          st[j][2] = -INFINITY; st[j][3] = -INFINITY;
         } else {
           st[j][0] = fast_valid<TIME>(c, col, keyA) ? st[j][0] : -INFINITY;
           st[j][1] = fast_valid<TIME>(c, col + 1, keyA) ? st[j][1] : -INFINITY;
@@ -1273,7 +1291,10 @@ extern "C" int egovlp_divided_attn_bwd(const void* qkv, const void* out, const v
     if (G.NPAD > 128) LAUNCH_BWD((fast_attn_bwd_kernel<false, 7, 2>), 7, 0);
     else LAUNCH_BWD((fast_attn_bwd_kernel<false, 4, 3>), 4, 0);
   } else {
-    LAUNCH_BWD((fast_attn_bwd_kernel<true, 4, 3>), 4, time_shift(G));
+    const char* we = getenv("EGOVLP_ATTN_TIME_BWD_WARPS");
+    const bool w8 = we && we[0] == '8';
+    if (w8) LAUNCH_BWD((fast_attn_bwd_kernel<true, 8, 2>), 8, time_shift(G));
+    else LAUNCH_BWD((fast_attn_bwd_kernel<true, 4, 3>), 4, time_shift(G));
   }
 #undef LAUNCH_BWD
   EGOVLP_CHECK_LAUNCH();

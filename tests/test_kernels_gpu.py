@@ -169,7 +169,7 @@ def test_cast_and_colsum(ops):
         assert rel_err(out, 1 + dy.float().sum(0)) < 1e-5
 
 
-@pytest.mark.parametrize("generic", [False, True, "tc"])
+@pytest.mark.parametrize("generic", [False, True, "tc", "w8"])
 @pytest.mark.parametrize("B,T,N,H,mode", [(2, 4, 196, 2, 1), (2, 4, 196, 2, 0), (1, 16, 196, 1, 0), (1, 16, 196, 1, 1),
                                           (2, 3, 4, 2, 0), (2, 3, 4, 2, 1), (3, 8, 50, 1, 0), (2, 1, 30, 1, 0),
                                           (2, 5, 196, 1, 0), (2, 8, 196, 1, 0), (1, 8, 196, 2, 1), (2, 16, 100, 1, 0),
@@ -181,6 +181,7 @@ def test_divided_attention_fwd_bwd(ops, B, T, N, H, mode, generic, monkeypatch):
     # False: default dispatch (mma.sync span kernels); "tc": tcgen05/TMEM space forward; True: generic group-id kernels
     monkeypatch.setenv("EGOVLP_ATTN_GENERIC", "1" if generic is True else "0")
     monkeypatch.setenv("EGOVLP_ATTN_TC", "1" if generic == "tc" else "0")
+    monkeypatch.setenv("EGOVLP_ATTN_TIME_BWD_WARPS", "8" if generic == "w8" else "4")   # both time-backward shapes
     S, D = 1 + T * N, 64 * H
     qkv = mk((B * S, 3 * D), 50 + T + mode, 1.0)
     scale = 0.125
