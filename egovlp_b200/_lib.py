@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libegovlp_b200.so")
+# EGOVLP_B200_LIB: A/B a differently built library from the tools/ benchmarks (never a fallback: it must exist too)
+LIB_PATH = os.environ.get("EGOVLP_B200_LIB") or os.path.join(_PKG, "lib", "libegovlp_b200.so")
 _lib = None
 
 

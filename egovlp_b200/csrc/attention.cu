@@ -708,9 +708,12 @@ __device__ __forceinline__ bool get_chunk(const FastCtx& c, int T, int r0, int p
   ch.np = min(CW, (c.NPAD - k0) >> 4);
   ch.mask = 0;
 #pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    ch.base[p] = k0 + 16 * p;
-    if (p < ch.np && k0 + 16 * p + 16 > (c.NP & ~15)) ch.mask |= 1u << p;
+  for (int p = 0; p < 4; ++p) ch.base[p] = k0 + 16 * p;
+  const int first_masked = c.NP & ~15;            // the pair holding the last patches, the CLS key and the padding
+  if (k0 + CW * 16 > first_masked) {              // only the tail chunk(s) pay for the mask bits
+#pragma unroll
+    for (int p = 0; p < CW; ++p)
+      if (p < ch.np && k0 + 16 * p + 16 > first_masked) ch.mask |= 1u << p;
   }
   return true;
 }
