@@ -7,6 +7,7 @@ Numerics layout: residual stream and LayerNorm statistics in fp32, GEMM operands
 TMEM), attention probabilities never leave the SM, losses in fp32.  fp32 master parameters are the autograd
 leaves; their bf16 GEMM copies come from `Bf16Cache` (refreshed when a parameter's version changes).
 """
+import os
 import torch
 
 from . import ops
@@ -19,7 +20,33 @@ def _empty(shape, dtype, like):
     return torch.empty(shape, dtype=dtype, device=like.device)
 
 
+class _ZeroArena:
+    """One zero-filled fp32 buffer per block backward, carved into the ~20 accumulators (split-K weight gradients, bias /
+    LayerNorm gradient vectors) that each used to cost a fill launch of its own.  Views keep the buffer alive."""
+
+    def __init__(self, n_floats, like):
+        self.buf = torch.zeros(n_floats, dtype=F32, device=like.device)
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.off + n > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 63) // 64 * 64                     # 256-byte aligned carve-outs
+        return v
+
+
+_arena = None
+
+
 def _zeros(shape, like):
+    if _arena is not None and _arena.buf.device == like.device:
+        v = _arena.take(shape)
+        if v is not None:
+            return v
     return torch.zeros(shape, dtype=F32, device=like.device)
 
 
@@ -201,6 +228,18 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         D = H * 64
         M = x2.shape[0]
         dy = dy.contiguous().view(M, D)
+        global _arena
+        _arena = _ZeroArena(2 * D * HID + 8 * D * D + HID + 24 * D + 32 * 64, dy)
+        try:
+            return SpaceTimeBlockFn._backward(ctx, dy, sv, B, T, N, H, HID, D, M, cache)
+        finally:
+            _arena = None
+
+    @staticmethod
+    def _backward(ctx, dy, sv, B, T, N, H, HID, D, M, cache):
+        (x2, n3, mean3, rstd3, qkv_t, a_t, lse_t, tr, n1, mean1, rstd1, qkv_s, a_s, lse_s, sr, n2, mean2, rstd2, u,
+         h) = sv[:20]
+        (n1w, n1b, sqw, sqb, spw, spb, tqw, tqb, tpw, tpb, n2w, n2b, f1w, f1b, f2w, f2b, n3w, n3b) = sv[20:]
         dy16, g_f2b = _byproducts_of(dy)                     # fc2 bias gradient = colsum(dy)
 
         # ---- MLP:  y = sr + fc2(gelu(fc1(LN2(sr))))
