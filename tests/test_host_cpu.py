@@ -151,3 +151,33 @@ def test_gather_semantics_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert all("OK" in o for o in outs)
+
+
+def test_bench_flop_model_matches_the_survey_and_the_oracle_counter():
+    """bench.py's algorithmic-FLOP model (the numerator of every roofline fraction it prints) equals SURVEY.md 8d's
+    figures, and its forward part equals torch's FLOP counter run on the oracle at a small shape."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    step, video, text = bench.flops_per_clip(16, 16)
+    assert abs(video / 1e9 - 739.177) < 0.01 and abs(text / 1e9 - 1.364) < 0.01 and abs(step / 1e9 - 2217.9) < 0.1
+    step4, video4, _ = bench.flops_per_clip(4, 16)
+    assert abs(video4 / 1e9 - 184.617) < 0.01 and abs(step4 / 1e9 - 557.0) < 0.1
+    cfg = bench.workload_config(type("A", (), {"frames": 16, "text_len": 16, "batch": 64})(), 8)
+    assert cfg["global_batch"] == 512 and cfg["parallelism"] == "dp8" and "workload" in cfg
+    # forward FLOPs of the tiny tower, counted by torch on the oracle, against the same formula
+    from torch.utils.flop_counter import FlopCounterMode
+    from oracle import reference_port as rp
+    from egovlp_b200 import synthetic as syn
+    d = syn.TINY_DIMS
+    sd = syn.seeded_state_dict(d, seed=0, text=False, proj=False)
+    vid = syn.synthetic_video(1, 4, seed=0, img=32)
+    with FlopCounterMode(display=False) as fc:
+        rp.video_tower(vid, sd, heads=2)
+    N = (32 // 16) ** 2
+    _, want, _ = bench.flops_per_clip(4, 8, N=N, D=128, H=2, HID=4 * 128, depth=2)
+    want -= 2 * 128 * 256                                     # no projection head in video_tower()
+    want -= 2 * 4 * N * 128 * 128 - 2 * 4 * N * 128 * (3 * 16 * 16)   # patch embed of a 16x16x3 patch: K = 768, not D
+    assert abs(fc.get_total_flops() - want) / want < 0.02, (fc.get_total_flops(), want)
