@@ -51,61 +51,63 @@ def _build_distilbert(text_params):
         return DistilBertModel(DistilBertConfig())
 
 
+_VIT_B16_FILE = "pretrained/jx_vit_base_p16_224-80ecf9dd.pth"
+
+
+def _build_video_tower(video_params, from_scratch):
+    """SpaceTimeTransformer exactly as the reference configures it (model/model.py:43-66): defaults for missing keys,
+    ImageNet ViT-B/16 weights for a tower that is not restored from a checkpoint, identity head / pre_logits / fc."""
+    kind = video_params['model']
+    if kind != "SpaceTimeTransformer":
+        raise NotImplementedError(f"{kind} not implemented")
+    opts = {'num_frames': 4, 'time_init': 'zeros', 'attention_style': 'frozen-in-time', 'arch_config': 'base_patch16_224'}
+    opts.update({k: video_params[k] for k in opts if k in video_params})
+    if opts.pop('arch_config') != 'base_patch16_224':
+        raise NotImplementedError
+    tower = SpaceTimeTransformer(**opts)
+    tower.head = tower.pre_logits = tower.fc = nn.Identity()      # `fc`: "backwards compatibility (old models)"
+    if from_scratch:
+        if os.path.exists(_VIT_B16_FILE):
+            vit = torch.load(_VIT_B16_FILE, map_location="cpu")
+            tower.load_state_dict(state_dict_data_parallel_fix(vit, tower.state_dict()), strict=False)
+        else:
+            warnings.warn(f"{_VIT_B16_FILE} not found: video tower keeps its random initialisation")
+    return tower
+
+
 class FrozenInTime(BaseModel):
     def __init__(self, video_params, text_params, projection_dim=256, load_checkpoint=None, projection='minimal',
                  load_temporal_fix='zeros'):
         super().__init__()
-        self.video_params = video_params
-        self.text_params = text_params
-        self.load_temporal_fix = load_temporal_fix
+        self.video_params, self.text_params, self.load_temporal_fix = video_params, text_params, load_temporal_fix
         if not text_params['pretrained']:
             raise NotImplementedError("Huggingface text models require pretrained init.")
-        if not self.text_params['model'].startswith('distilbert'):
+        if not text_params['model'].startswith('distilbert'):
             raise NotImplementedError(f"{text_params['model']}: only the DistilBERT text tower is implemented")
         self.text_model = _build_distilbert(text_params)
-        self.text_model.train()
+        self.text_model.train()                                   # as the reference: HF dropouts active while training
+        restoring = load_checkpoint not in ("", None)
+        self.video_model = _build_video_tower(video_params, from_scratch=not restoring)
 
-        if video_params['model'] != "SpaceTimeTransformer":
-            raise NotImplementedError(f"{video_params['model']} not implemented")
-        num_frames = video_params.get('num_frames', 4)
-        time_init = video_params.get('time_init', 'zeros')
-        attention_style = video_params.get('attention_style', 'frozen-in-time')
-        arch_config = video_params.get('arch_config', 'base_patch16_224')
-        if arch_config != 'base_patch16_224':
-            raise NotImplementedError
-        model = SpaceTimeTransformer(num_frames=num_frames, time_init=time_init, attention_style=attention_style)
-        model.head = nn.Identity()
-        model.pre_logits = nn.Identity()
-        ftr_dim = model.embed_dim
-        if load_checkpoint in ["", None]:
-            vit_path = "pretrained/jx_vit_base_p16_224-80ecf9dd.pth"
-            if os.path.exists(vit_path):
-                vit_checkpoint = torch.load(vit_path, map_location="cpu")
-                model.load_state_dict(state_dict_data_parallel_fix(vit_checkpoint, model.state_dict()), strict=False)
-            else:
-                warnings.warn(f"{vit_path} not found: video tower keeps its random initialisation")
-        self.video_model = model
-        self.video_model.fc = nn.Identity()
-
-        if projection == 'minimal':
-            txt_proj = nn.Sequential(nn.ReLU(), nn.Linear(self.text_model.config.hidden_size, projection_dim))
-            vid_proj = nn.Sequential(nn.Linear(ftr_dim, projection_dim))
+        if projection == 'minimal':                               # project both towers to the common embedding
+            self.txt_proj = nn.Sequential(nn.ReLU(), nn.Linear(self.text_model.config.hidden_size, projection_dim))
+            self.vid_proj = nn.Sequential(nn.Linear(self.video_model.embed_dim, projection_dim))
         elif projection == '':
-            txt_proj, vid_proj = nn.Identity(), nn.Identity()
+            self.txt_proj, self.vid_proj = nn.Identity(), nn.Identity()
         else:
             raise NotImplementedError
-        self.txt_proj = txt_proj
-        self.vid_proj = vid_proj
         object.__setattr__(self, "_bf16_cache", self.video_model._bf16_cache)
+        if restoring:
+            self._restore(load_checkpoint)
 
-        if load_checkpoint not in ["", None]:
-            local_rank = int(os.environ.get('LOCAL_RANK', 0))
-            map_loc = 'cuda:{}'.format(local_rank) if torch.cuda.is_available() else 'cpu'
-            checkpoint = torch.load(load_checkpoint, map_location=map_loc, weights_only=False)
-            state_dict = checkpoint['state_dict']
-            new_state_dict = state_dict_data_parallel_fix(state_dict, self.state_dict())
-            new_state_dict = self._inflate_positional_embeds(new_state_dict)
-            self.load_state_dict(new_state_dict, strict=True)
+    def _restore(self, path):
+        """model/model.py:88-95: a trainer checkpoint, saved with or without the DataParallel prefix and possibly with
+        a different number of frames."""
+        rank = int(os.environ.get('LOCAL_RANK', 0))
+        where = f'cuda:{rank}' if torch.cuda.is_available() else 'cpu'
+        saved = torch.load(path, map_location=where, weights_only=False)['state_dict']
+        saved = self._inflate_positional_embeds(state_dict_data_parallel_fix(saved, self.state_dict()))
+        self.load_state_dict(saved, strict=True)
 
     def set_device(self, device):
         self.device = device

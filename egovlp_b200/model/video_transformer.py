@@ -23,10 +23,10 @@ class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
         super().__init__()
         assert drop == 0., "dropout inside the video tower is not implemented (reference configs use 0)"
-        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
-        self.act = act_layer()
-        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
-        self.drop = nn.Dropout(drop)
+        assert act_layer is nn.GELU, "the fc1 epilogue implements GELU(erf) only"
+        hidden = hidden_features or in_features
+        # parameter containers only (keys mlp.fc1.*, mlp.fc2.*): GELU and the two GEMMs run in the fused epilogues
+        self.fc1, self.fc2 = nn.Linear(in_features, hidden), nn.Linear(hidden, out_features or in_features)
 
 
 class VideoPatchEmbed(nn.Module):
@@ -54,11 +54,10 @@ class VarAttention(nn.Module):
         self.scale = (dim // num_heads) ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.proj = nn.Linear(dim, dim)
-        if initialize == 'zeros':
-            self.qkv.weight.data.fill_(0)
-            self.qkv.bias.data.fill_(0)
-            self.proj.weight.data.fill_(1)
-            self.proj.bias.data.fill_(0)
+        if initialize == 'zeros':                      # reference :90-96: the temporal branch starts as the zero map
+            with torch.no_grad():
+                for t, v in ((self.qkv.weight, 0.), (self.qkv.bias, 0.), (self.proj.weight, 1.), (self.proj.bias, 0.)):
+                    t.fill_(v)
 
 
 class SpaceTimeBlock(nn.Module):
@@ -130,7 +129,6 @@ class SpaceTimeTransformer(nn.Module):
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, self.patches_per_frame + 1, embed_dim))
         self.temporal_embed = nn.Parameter(torch.zeros(1, num_frames, embed_dim))
-        self.pos_drop = nn.Dropout(p=drop_rate)
         self.blocks = nn.ModuleList([
             SpaceTimeBlock(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
                            qk_scale=qk_scale, drop=drop_rate, attn_drop=attn_drop_rate, drop_path=0.,
@@ -141,31 +139,18 @@ class SpaceTimeTransformer(nn.Module):
         self.head = nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity()
         nn.init.trunc_normal_(self.pos_embed, std=.02)
         nn.init.trunc_normal_(self.cls_token, std=.02)
-        if num_frames == 1:
-            self.apply(self._init_weights)
+        if num_frames == 1:                            # reference :268-270: image mode re-initialises every layer
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.trunc_normal_(m.weight, std=.02)
+                    if m.bias is not None:
+                        nn.init.zeros_(m.bias)
+                elif isinstance(m, nn.LayerNorm):
+                    nn.init.zeros_(m.bias)
+                    nn.init.ones_(m.weight)
         self.einops_from_space, self.einops_to_space = 'b (f n) d', '(b f) n d'
         self.einops_from_time, self.einops_to_time = 'b (f n) d', '(b n) f d'
         object.__setattr__(self, "_bf16_cache", engine.Bf16Cache())
-
-    def _init_weights(self, m):
-        if isinstance(m, nn.Linear):
-            nn.init.trunc_normal_(m.weight, std=.02)
-            if m.bias is not None:
-                nn.init.constant_(m.bias, 0)
-        elif isinstance(m, nn.LayerNorm):
-            nn.init.constant_(m.bias, 0)
-            nn.init.constant_(m.weight, 1.0)
-
-    @torch.jit.ignore
-    def no_weight_decay(self):
-        return {'pos_embed', 'cls_token'}
-
-    def get_classifier(self):
-        return self.head
-
-    def reset_classifier(self, num_classes, global_pool=''):
-        self.num_classes = num_classes
-        self.head = nn.Linear(self.embed_dim, num_classes) if num_classes > 0 else nn.Identity()
 
     def forward_tokens(self, x):
         """All tokens after the 12 blocks, [B, S, D] fp32 (before the final norm)."""
