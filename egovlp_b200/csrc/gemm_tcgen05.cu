@@ -44,6 +44,8 @@ struct EpiParams {
   int col_scale_ncols;
   int res_row_mod;  // 0: residual row = m; else residual row = m % res_row_mod (broadcast table)
   float* colsum;    // optional fp32 [N]: accumulates the column sums of the stored values (bias gradient)
+  float* colsum_a;  // optional fp32 [M], MN-major A / MN-major B (wgrad) only: accumulates sum_k A[k, m], i.e. the bias
+                    // gradient of the Linear whose weight gradient this GEMM computes, from the A tiles already in smem
   int debug_no_loads;  // profiling aid (EGOVLP_GEMM_DEBUG_NOLOADS=1): skip the TMA loads, MMAs run on stale smem
 };
 
@@ -154,7 +156,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
-      mbar_init(empty_bar + 8 * s, 1);
+      // a stage is released by the MMA commit and, when the A tiles are column-summed, by the two summing warps too
+      mbar_init(empty_bar + 8 * s, (A_MN && B_MN && !TWO && ep.colsum_a) ? 3 : 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
@@ -252,6 +255,56 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if ((warp == 2 || warp == 3) && A_MN && B_MN && !TWO && ep.colsum_a != nullptr) {
+    // ===================== column sums of A (wgrad only): bias gradient for free =====================
+    // A stage holds A as two slabs [64 k-rows][64 m-columns] (128 B rows, 16-byte chunks XOR-swizzled by row & 7).
+    // Warp 2 sums slab 0, warp 3 slab 1: lane = (row & 3 group, chunk); each lane keeps 8 fp32 column sums.  Only the
+    // units of the first n-block do it, so every (k-range, m-block) is summed exactly once across the grid.
+    const int slab = warp - 2, chunk = lane & 7, rsub = lane >> 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int unit = worker; unit < num_units; unit += num_workers) {
+      const int split = unit / num_tiles, tile = unit - split * num_tiles;
+      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
+      const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
+      const bool mine = n_blk == 0;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        if (mine) {
+          const uint32_t slab_base = sA + stage * A_STAGE_BYTES + slab * MN_ATOM_BYTES;
+#pragma unroll 4
+          for (int i = 0; i < 16; ++i) {
+            const int r = rsub + 4 * i;
+            uint32_t v0, v1, v2, v3;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                         : "r"(slab_base + r * 128 + ((chunk ^ (r & 7)) << 4)));
+            acc[0] += __uint_as_float(v0 << 16); acc[1] += __uint_as_float(v0 & 0xffff0000u);
+            acc[2] += __uint_as_float(v1 << 16); acc[3] += __uint_as_float(v1 & 0xffff0000u);
+            acc[4] += __uint_as_float(v2 << 16); acc[5] += __uint_as_float(v2 & 0xffff0000u);
+            acc[6] += __uint_as_float(v3 << 16); acc[7] += __uint_as_float(v3 & 0xffff0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (mine) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+        }
+        const int col = m_blk * BLOCK_M + slab * 64 + chunk * 8;
+        if (lane < 8 && col < M) {            // M % 8 == 0 is checked by the host
+          red_add_v4(ep.colsum_a + col, acc[0], acc[1], acc[2], acc[3]);
+          red_add_v4(ep.colsum_a + col + 4, acc[4], acc[5], acc[6], acc[7]);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -475,6 +528,10 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   ep.out_mode = e->out_mode; ep.act = e->act; ep.alpha = e->alpha;
   ep.col_scale = e->col_scale; ep.col_scale_ncols = e->col_scale_ncols; ep.res_row_mod = e->res_row_mod;
   ep.colsum = e->colsum;
+  ep.colsum_a = e->colsum_a;
+  EGOVLP_CHECK_ARG(!e->colsum_a || (a_mn_major && b_mn_major && N % 256 == 0 && M % 8 == 0 &&
+                                    (reinterpret_cast<uintptr_t>(e->colsum_a) & 15) == 0),
+                   "gemm: colsum_a needs the MN/MN (wgrad) form with N % 256 == 0, M % 8 == 0 and a 16B-aligned vector");
   {
     const char* dbg = getenv("EGOVLP_GEMM_DEBUG_NOLOADS");
     ep.debug_no_loads = (dbg && dbg[0] == '1') ? 1 : 0;

@@ -37,7 +37,7 @@ def profile_gemm(enable):
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, out2=None, act=0, alpha=1.0,
-         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0, colsum=None):
+         col_scale=1.0, col_scale_ncols=0, accumulate=False, split_k=1, res_row_mod=0, colsum=None, colsum_a=None):
     """out = epi(A @ B^T).  a: [M,K] (or [K,M] if a_mn), b: [N,K] (or [K,N] if b_mn); 2-D, last-dim contiguous.
     out: bf16 or fp32 [M,N]; accumulate=True -> fp32 atomic add into `out` (required for split_k>1)."""
     _chk(a, BF16, "a"); _chk(b, BF16, "b")
@@ -75,6 +75,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     if colsum is not None:
         _chk(colsum, F32, "colsum"); assert colsum.numel() == N
     e.colsum = colsum.data_ptr() if colsum is not None else None
+    if colsum_a is not None:                 # wgrad form only: column sums of A accumulated from the smem tiles
+        _chk(colsum_a, F32, "colsum_a"); assert a_mn and b_mn and colsum_a.numel() == M
+    e.colsum_a = colsum_a.data_ptr() if colsum_a is not None else None
     if _gemm_prof is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

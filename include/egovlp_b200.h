@@ -58,6 +58,9 @@ typedef struct egovlp_gemm_epilogue {
   int col_scale_ncols;
   int res_row_mod; /* 0: residual row = m; >0: residual row = m % res_row_mod (broadcast [res_row_mod, ldr] table) */
   float* colsum;   /* optional fp32 [N]: ACCUMULATES the column sums of the stored values (bias gradient of dy) */
+  float* colsum_a; /* optional fp32 [M], only with a_mn_major && b_mn_major (the token-contraction weight gradient
+                      dW = dy^T x): ACCUMULATES sum_k A[k, m] = the bias gradient of the same Linear, summed from the
+                      A tiles while they sit in shared memory for the MMA (no extra pass over dy) */
 } egovlp_gemm_epilogue;
 
 int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, const void* B, int b_mn_major, long long ldb,

@@ -63,6 +63,11 @@ def test_gemm_both_mn_major_wgrad(ops, Mtok, N, Kin, split, gemm_mode):
     ops.gemm(dy, x, out, a_mn=True, b_mn=True, accumulate=True, split_k=split)
     ref = base + dy.float().t() @ x.float()
     assert rel_err(out, ref) < 2e-5
+    if Kin % 256 == 0:        # fused bias gradient: column sums of dy taken from the smem tiles of the same GEMM
+        out2, db = base.clone(), torch.full((N,), 0.5, device="cuda")
+        ops.gemm(dy, x, out2, a_mn=True, b_mn=True, accumulate=True, split_k=split, colsum_a=db)
+        assert rel_err(out2, ref) < 2e-5
+        assert rel_err(db, 0.5 + dy.float().sum(0)) < 1e-5
 
 
 def test_gemm_epilogues(ops, gemm_mode):
