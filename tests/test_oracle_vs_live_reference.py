@@ -119,3 +119,58 @@ def test_attention_core_matches_var_attention_module():
         core = rp.divided_attention_core(qkv, H, T, N, mode)
         got = torch.nn.functional.linear(core, attn.proj.weight, attn.proj.bias)
         close(got, want, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fix", ["zeros", "interp", "bilinear"])
+@pytest.mark.parametrize("load_f,curr_f", [(4, 16), (16, 4), (8, 8), (1, 4)])
+def test_temporal_embed_inflation_matches_reference(fix, load_f, curr_f):
+    """FrozenInTime._inflate_positional_embeds (model/model.py:145-187) of the mirror vs the reference's, called on the
+    same stand-in object (the method only touches video_params, load_temporal_fix and state_dict())."""
+    import types
+    mm, _, _ = ref_shim.modules()
+    from egovlp_b200.model.model import FrozenInTime
+    g = torch.Generator().manual_seed(load_f * 100 + curr_f)
+    curr = {"video_model.temporal_embed": torch.zeros(1, curr_f, 12), "video_model.pos_embed": torch.zeros(1, 5, 12)}
+
+    def stand_in():
+        return types.SimpleNamespace(video_params={"num_frames": curr_f, "model": "SpaceTimeTransformer"},
+                                     load_temporal_fix=fix, state_dict=lambda: curr)
+
+    def loaded():
+        gg = torch.Generator().manual_seed(7)
+        return {"video_model.temporal_embed": torch.randn(1, load_f, 12, generator=gg),
+                "video_model.pos_embed": torch.randn(1, 5, 12, generator=gg), "other": torch.ones(3)}
+
+    got = FrozenInTime._inflate_positional_embeds(stand_in(), loaded())
+    if fix == "interp" and load_f < curr_f:
+        # the reference passes align_corners=True with mode='nearest' (:172-175), which torch rejects: its 'interp' mode
+        # cannot inflate at all.  The mirror keeps the mode usable (plain nearest-neighbour along the frame axis).
+        with pytest.raises(ValueError):
+            mm.FrozenInTime._inflate_positional_embeds(stand_in(), loaded())
+        src = loaded()["video_model.temporal_embed"]
+        want_te = torch.nn.functional.interpolate(src.unsqueeze(0), (curr_f, 12), mode="nearest").squeeze(0)
+        torch.testing.assert_close(got["video_model.temporal_embed"], want_te, rtol=0, atol=0)
+        return
+    want = mm.FrozenInTime._inflate_positional_embeds(stand_in(), loaded())
+    assert set(got) == set(want)
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        torch.testing.assert_close(got[k], want[k], rtol=0, atol=0)
+    bad = loaded()
+    bad["video_model.pos_embed"] = torch.zeros(1, 9, 12)
+    for cls in (mm.FrozenInTime, FrozenInTime):
+        with pytest.raises(NotImplementedError):
+            cls._inflate_positional_embeds(stand_in(), dict(bad))
+
+
+def test_data_parallel_prefix_fix_matches_reference():
+    ref_shim.install()
+    from utils.util import state_dict_data_parallel_fix as ref_fix
+    from egovlp_b200.model.model import state_dict_data_parallel_fix as our_fix
+    from collections import OrderedDict
+    plain = OrderedDict((k, torch.tensor(float(i))) for i, k in enumerate(["a.w", "a.b", "c"]))
+    dp = OrderedDict(("module." + k, v) for k, v in plain.items())
+    for load, curr in ((plain, plain), (dp, plain), (plain, dp), (dp, dp)):
+        want, got = ref_fix(OrderedDict(load), curr), our_fix(OrderedDict(load), curr)
+        assert list(got.keys()) == list(want.keys())
+        assert all(torch.equal(got[k], want[k]) for k in want)
