@@ -174,3 +174,17 @@ def test_data_parallel_prefix_fix_matches_reference():
         want, got = ref_fix(OrderedDict(load), curr), our_fix(OrderedDict(load), curr)
         assert list(got.keys()) == list(want.keys())
         assert all(torch.equal(got[k], want[k]) for k in want)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_egomcq_accuracy_metrics_matches_reference(seed):
+    ref_shim.install()
+    import model.metric as ref_metric
+    from egovlp_b200.model.metric import egomcq_accuracy_metrics
+    g = torch.Generator().manual_seed(seed)
+    Q = 50
+    preds = torch.randn(Q, 5, generator=g)
+    preds[3, 2] = preds[3, 4] = preds[3].max() + 1            # a tie: argmax must resolve identically
+    labels = torch.randint(0, 5, (Q,), generator=g)
+    types = torch.randint(1, 3, (Q,), generator=g)
+    assert egomcq_accuracy_metrics(preds, labels, types) == ref_metric.egomcq_accuracy_metrics(preds, labels, types)
