@@ -18,8 +18,15 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIB_DIR, "libegovlp_b200.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+# IEEE fp32 (no --use_fast_math: no approximate division / sqrt / exp, no flush-to-zero) where the reference computes in
+# fp32 and the results are compared at fp32 rounding level or bit-exactly: losses, ranking metrics, EgoMCQ, AdamW.
+IEEE_SOURCES = {"loss.cu", "retrieval.cu", "optim.cu"}
+
+
+def flags_for(src):
+    return NVCC_FLAGS + ([] if os.path.basename(src) in IEEE_SOURCES else ["--use_fast_math"])
 
 
 def nvcc():
@@ -47,7 +54,7 @@ def build(force=False, verbose=False):
         o = os.path.join(OBJ, os.path.basename(s)[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc()] + flags_for(s) + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -8,6 +8,9 @@ TMEM), attention probabilities never leave the SM, losses in fp32.  fp32 master 
 leaves; their bf16 GEMM copies come from `Bf16Cache` (refreshed when a parameter's version changes).
 """
 import os
+import threading
+import weakref
+
 import torch
 
 from . import ops
@@ -39,60 +42,171 @@ class _ZeroArena:
         return v
 
 
-_arena = None
+_tls = threading.local()        # per autograd thread (= per device): the arena of the block backward in progress
 
 
 def _zeros(shape, like):
-    if _arena is not None and _arena.buf.device == like.device:
-        v = _arena.take(shape)
+    arena = getattr(_tls, "arena", None)
+    if arena is not None and arena.buf.device == like.device:
+        v = arena.take(shape)
         if v is not None:
             return v
     return torch.zeros(shape, dtype=F32, device=like.device)
 
 
+# Generation counter of "some optimizer stepped": bumped by a global torch.optim post-step hook, so that bf16 copies
+# are rebuilt even when the optimizer wrote through `p.data` (transformers.AdamW 4.x, apex), which does not bump
+# `p._version`.  The fused egovlp_b200.optim.AdamW refreshes the copies itself (same kernel pass) and is exempt.
+_GEN = 0
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    global _GEN
+    if not getattr(optimizer, "_egovlp_fused", False):
+        _GEN += 1
+
+
+try:                                                          # torch >= 2.0
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_hook
+    _reg_hook(_on_optimizer_step)
+except ImportError:                                           # pragma: no cover
+    pass
+
+
+class _CastEntry:
+    __slots__ = ("ref", "t16", "version", "ptr", "gen", "trusted")
+
+    def __init__(self, p, t16):
+        self.ref, self.t16 = weakref.ref(p), t16
+        self.version, self.ptr, self.gen, self.trusted = -1, 0, -1, False
+
+    def stamp(self, p, trusted=False):
+        self.version, self.ptr, self.gen, self.trusted = p._version, p.data_ptr(), _GEN, trusted
+
+    def current(self, p):
+        return (self.ref() is p and self.version == p._version and self.ptr == p.data_ptr() and self.gen == _GEN
+                and self.t16.device == p.device)
+
+
+_SHADOWS = {}          # id(param) -> _CastEntry: lets the fused AdamW write the bf16 copy in its own pass
+
+
+def shadow_entry(p):
+    ent = _SHADOWS.get(id(p))
+    return ent if ent is not None and ent.ref() is p and ent.t16.device == p.device else None
+
+
 class Bf16Cache:
-    """bf16 copies of fp32 parameters, refreshed lazily when the parameter changed (optimizer step / load)."""
+    """bf16 GEMM-operand copies of the fp32 master parameters.
+
+    * `get(p)` returns the copy, re-casting when the parameter object, its storage, its version or the global
+      optimizer generation changed (entries hold a weak reference, so a recycled `id()` cannot alias a dead parameter).
+    * `refresh()` -- called at the top of every TRAINING forward -- re-casts every known copy in ONE launch
+      (egovlp_cast_multi_f32_to_bf16) unless the fused AdamW just wrote it, so an update made through `p.data` by any
+      optimizer / EMA is always seen by the next training step."""
 
     def __init__(self):
         self._store = {}
+        self._cats = {}
+        self._table = None
+
+    def _entry(self, p, t16_factory):
+        ent = self._store.get(id(p))
+        if ent is None or ent.ref() is not p or ent.t16.device != p.device:
+            ent = _CastEntry(p, t16_factory())
+            self._store[id(p)] = ent
+            _SHADOWS[id(p)] = ent
+            self._table = None
+        if not ent.current(p):
+            ops.cast_bf16(p.detach().contiguous(), ent.t16)
+            ent.stamp(p)
+        return ent
 
     def get(self, p, shape=None):
-        key = id(p)
-        ent = self._store.get(key)
-        if ent is None or ent[0] != p._version or ent[1].device != p.device or ent[2] != p.data_ptr():
-            src = p.detach().contiguous()
-            ent = (p._version, ops.cast_bf16(src), p.data_ptr())
-            self._store[key] = ent
-        t = ent[1]
+        t = self._entry(p, lambda: torch.empty(p.shape, dtype=BF16, device=p.device)).t16
         return t.view(shape) if shape is not None else t
 
     def cat(self, name, params):
-        """bf16 concat along dim 0 of several parameters (DistilBERT q/k/v -> one [3D, D] operand)."""
-        vers = tuple((p._version, p.data_ptr()) for p in params)
-        ent = self._store.get(name)
-        if ent is None or ent[0] != vers:
-            ent = (vers, torch.cat([ops.cast_bf16(p.detach().contiguous()) for p in params], dim=0))
-            self._store[name] = ent
-        return ent[1]
+        """bf16 concat along dim 0 of several parameters (DistilBERT q/k/v -> one [3D, D] operand): every part is a cache
+        entry whose copy is a slice of one buffer, so `refresh()` keeps the concatenation current too."""
+        buf = self._cats.get(name)
+        rows = sum(p.shape[0] for p in params)
+        if buf is None or buf.device != params[0].device or buf.shape[0] != rows:
+            buf = torch.empty((rows,) + tuple(params[0].shape[1:]), dtype=BF16, device=params[0].device)
+            self._cats[name] = buf
+            for p in params:
+                self._store.pop(id(p), None)
+        r = 0
+        for p in params:
+            sl = buf[r:r + p.shape[0]]
+            self._entry(p, lambda sl=sl: sl)
+            r += p.shape[0]
+        return buf
+
+    def refresh(self):
+        """Bring every cached copy up to date with one multi-tensor cast (no-op for copies the fused AdamW just wrote)."""
+        live = []
+        for key, ent in list(self._store.items()):
+            p = ent.ref()
+            if p is None or ent.t16.device != p.device:
+                del self._store[key]
+                if _SHADOWS.get(key) is ent:
+                    del _SHADOWS[key]
+                self._table = None
+                continue
+            if not (ent.trusted and ent.current(p)):
+                live.append((p, ent))
+        if not live:
+            return
+        key = tuple((p.data_ptr(), ent.t16.data_ptr(), p.numel()) for p, ent in live)
+        if self._table is None or self._table[0] != key:
+            self._table = (key,) + ops.build_cast_table([(p.detach(), ent.t16) for p, ent in live])
+        ops.cast_multi(*self._table[1:])
+        for p, ent in live:
+            ent.stamp(p)
 
     def clear(self):
+        for key, ent in self._store.items():
+            if _SHADOWS.get(key) is ent:
+                del _SHADOWS[key]
         self._store.clear()
+        self._cats.clear()
+        self._table = None
 
 
 # By-products of an fp32 gradient tensor handed between consecutive Functions: its bf16 twin (saves one cast pass per
-# block) and its column sums (the next block's fc2 bias gradient; saves one read of the tensor per block).  Keyed by
-# the tensor's storage + shape and consumed once, so a gradient that autograd re-materialised is simply recomputed.
+# block) and its column sums (the next block's fc2 bias gradient; saves one read of the tensor per block).  An entry
+# holds the fp32 tensor itself, so its storage cannot be recycled for another tensor while the entry exists, and the
+# tensor's version, so a gradient that autograd accumulated into in place (a block output with two consumers) is
+# recognised and simply recomputed.  One slot per device; cleared when a video forward / backward starts.
 _twin = {}
+_twin_lock = threading.Lock()
 
 
 def _publish_twin(t32, t16, colsum=None):
-    _twin.clear()
-    _twin[(t32.data_ptr(), tuple(t32.shape))] = (t16, colsum)
+    with _twin_lock:
+        _twin[t32.device.index] = (t32, t32._version, t16, colsum)
+
+
+def _clear_twin(device):
+    with _twin_lock:
+        _twin.pop(device.index, None)
+
+
+def _take_twin(t32):
+    with _twin_lock:
+        ent = _twin.pop(t32.device.index, None)
+    if ent is None:
+        return None, None
+    src, version, t16, colsum = ent
+    same = (src.data_ptr() == t32.data_ptr() and src.numel() == t32.numel() and src._version == version
+            and t32.dtype == src.dtype and t32.is_contiguous())
+    return (t16, colsum) if same else (None, None)
 
 
 def _byproducts_of(t32):
     """-> (bf16 twin, column sums [D]) of an fp32 [M, D] gradient, from the producer if it published them."""
-    t16, colsum = _twin.pop((t32.data_ptr(), tuple(t32.shape)), (None, None))
+    t16, colsum = _take_twin(t32)
     if t16 is None:
         t16 = ops.cast_bf16(t32.contiguous())
     if colsum is None:
@@ -101,7 +215,7 @@ def _byproducts_of(t32):
 
 
 def _bf16_of(t32):
-    t16, _ = _twin.pop((t32.data_ptr(), tuple(t32.shape)), (None, None))
+    t16, _ = _take_twin(t32)
     if t16 is None:
         t16 = ops.cast_bf16(t32.contiguous())
     return t16
@@ -150,6 +264,7 @@ class PatchEmbedFn(torch.autograd.Function):
     def forward(ctx, video, cls_token, pos_embed, temporal_embed, w, b, cache, norm=None):
         B, T, C, H, W = video.shape
         D, _, P, _ = w.shape
+        _clear_twin(w.device)
         N = (H // P) * (W // P)
         S = 1 + T * N
         K = C * P * P
@@ -194,13 +309,15 @@ class SpaceTimeBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dims, eps, cache, *p):
         (n1w, n1b, sqw, sqb, spw, spb, tqw, tqb, tpw, tpb, n2w, n2b, f1w, f1b, f2w, f2b, n3w, n3b) = p
-        B, T, N, H = dims
+        B, T, N, H, grad_mode = dims
         D = H * 64
         S = 1 + T * N
         M = B * S
         HID = f1w.shape[0]
         x2 = x.contiguous().view(M, D)
-        train = any(ctx.needs_input_grad)
+        # `grad_mode` = torch.is_grad_enabled() at the call site: inside Function.forward grad mode is always off and
+        # needs_input_grad reflects requires_grad of the parameters even under torch.no_grad()
+        train = grad_mode and any(ctx.needs_input_grad)
 
         def ln(inp, w, b):
             y = _empty((M, D), BF16, inp)
@@ -243,12 +360,11 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         D = H * 64
         M = x2.shape[0]
         dy = dy.contiguous().view(M, D)
-        global _arena
-        _arena = _ZeroArena(2 * D * HID + 8 * D * D + HID + 24 * D + 32 * 64, dy)
+        _tls.arena = _ZeroArena(2 * D * HID + 8 * D * D + HID + 24 * D + 32 * 64, dy)
         try:
             return SpaceTimeBlockFn._backward(ctx, dy, sv, B, T, N, H, HID, D, M, cache)
         finally:
-            _arena = None
+            _tls.arena = None
 
     @staticmethod
     def _backward(ctx, dy, sv, B, T, N, H, HID, D, M, cache):
@@ -332,6 +448,7 @@ class ClsHeadFn(torch.autograd.Function):
     def backward(ctx, dout):
         B, S, D = ctx.shape
         dout = dout.contiguous().float()
+        _clear_twin(dout.device)
         g_pw = g_pb = None
         if ctx.has_proj:
             x, mean, rstd, nw, y16, pw = ctx.saved_tensors
@@ -367,6 +484,10 @@ class TextTowerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, input_ids, attention_mask, heads, eps, tokens_mode, cache, drop, *p):
+        """`tokens_mode`: False / True, or a (tokens_mode, grad_mode) pair -- see SpaceTimeBlockFn.forward."""
+        grad_mode = True
+        if isinstance(tokens_mode, tuple):
+            tokens_mode, grad_mode = tokens_mode
         word, pos, elw, elb = p[:4]
         pw, pb = p[-2:]
         layers = [p[4 + 16 * i: 4 + 16 * (i + 1)] for i in range((len(p) - 6) // 16)]
@@ -376,7 +497,7 @@ class TextTowerFn(torch.autograd.Function):
         ids = input_ids.contiguous().to(torch.int64)
         mask = attention_mask.contiguous().to(torch.int64)
         dev = word
-        train = any(ctx.needs_input_grad)
+        train = grad_mode and any(ctx.needs_input_grad)
         saved = []
         p_hid, p_att = (float(drop[0]), float(drop[1])) if drop else (0.0, 0.0)
         seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if (p_hid > 0 or p_att > 0) else 0
@@ -417,14 +538,19 @@ class TextTowerFn(torch.autograd.Function):
             saved += [x16, qkv, ctxv, sa, m1, r1, x1_16, u, hh, ff, m2, r2]
             x, x16 = xn, xn16
         rows, stride = (M, D) if tokens_mode else (B, L * D)
-        r16 = _empty((rows, D), BF16, dev)
-        ops.relu_rows_fwd(x, stride, r16, rows, D)
-        out = _empty((rows, pw.shape[0]), F32, dev)
-        ops.gemm(r16, cache.get(pw), out, bias=pb.detach())
+        if pw is None:                 # projection='' (nn.Identity, model/model.py:80-82): the hidden state itself
+            r16 = None
+            out = x if tokens_mode else x.view(B, L * D)[:, :D].clone()
+        else:
+            r16 = _empty((rows, D), BF16, dev)
+            ops.relu_rows_fwd(x, stride, r16, rows, D)
+            out = _empty((rows, pw.shape[0]), F32, dev)
+            ops.gemm(r16, cache.get(pw), out, bias=pb.detach())
         if train:
             ctx.meta = (B, L, D, heads, tokens_mode, len(layers), len(saved), p_hid, p_att, seed)
             ctx.cache = cache
-            ctx.save_for_backward(ids, mask, x, r16, *saved, *p)
+            ctx.has_proj = pw is not None
+            ctx.save_for_backward(ids, mask, x, r16, *saved, *p[:len(p) - (0 if pw is not None else 2)])
         return out.view(B, L, -1) if tokens_mode else out
 
     @staticmethod
@@ -436,18 +562,27 @@ class TextTowerFn(torch.autograd.Function):
         saved = list(sv[4:4 + n_saved])
         p = sv[4 + n_saved:]
         word, pos, elw, elb = p[:4]
-        pw, pb = p[-2:]
         layers = [p[4 + 16 * i: 4 + 16 * (i + 1)] for i in range(n_layers)]
         M = B * L
-        Pd = pw.shape[0]
         rows, stride = (M, D) if tokens_mode else (B, L * D)
-        dout = dout.contiguous().float().view(rows, Pd)
-        d16 = ops.cast_bf16(dout)
-        g_pw, g_pb = wgrad(d16, r16, Pd, D), bgrad(dout)
-        dr = _empty((rows, D), F32, dout)
-        ops.gemm(d16, cache.get(pw), dr, b_mn=True)
-        dx = _zeros((M, D), dout)
-        ops.relu_rows_bwd(x_last, stride, dr, dx, rows, D)
+        if ctx.has_proj:
+            pw, pb = p[-2:]
+            Pd = pw.shape[0]
+            dout = dout.contiguous().float().view(rows, Pd)
+            d16 = ops.cast_bf16(dout)
+            g_pw, g_pb = wgrad(d16, r16, Pd, D), bgrad(dout)
+            dr = _empty((rows, D), F32, dout)
+            ops.gemm(d16, cache.get(pw), dr, b_mn=True)
+            dx = _zeros((M, D), dout)
+            ops.relu_rows_bwd(x_last, stride, dr, dx, rows, D)
+        else:
+            g_pw = g_pb = None
+            dout = dout.contiguous().float().view(rows, D)
+            if tokens_mode:
+                dx = dout
+            else:
+                dx = _zeros((M, D), dout)
+                dx.view(B, L * D)[:, :D].copy_(dout)
         grads = []
         for li in reversed(range(n_layers)):
             (qw, qb, kw, kb, vw, vb, ow, ob, sw, sb, l1w, l1b, l2w, l2b, fw, fb) = layers[li]

@@ -13,8 +13,9 @@ class NormSoftmaxLoss(nn.Module):
 
     def forward(self, x):
         G = x.shape[0]
-        assert x.shape == (G, G)
-        mask = ops.positives_mask_from_sims(None, None, G, 0) if x.is_cuda else None
+        if x.dim() != 2 or x.shape[1] != G:
+            raise NotImplementedError(f"NormSoftmaxLoss: square similarity matrix expected, got {tuple(x.shape)}")
+        mask = ops.positives_mask_from_sims(None, None, G, 0, device=x.device)
         return engine.NceLossFn.apply(x, mask, self.temperature)
 
 

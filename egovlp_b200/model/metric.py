@@ -10,20 +10,16 @@ def egomcq_predict(text_embeds, video_embeds):
 
 
 def egomcq_accuracy_metrics(preds, labels, types):
-    """Same contract as the reference: preds [Q, K] scores, labels [Q], types [Q]; per-type accuracy in %.
-    The reference zips ["Intra-video", "Inter-video"] with the SORTED unique type ids (:220-222); kept as is."""
+    """Same contract as the reference (model/metric.py:218-234): preds [Q, K] scores, labels [Q], types [Q] -> accuracy
+    in % per question type, as tensor expressions (one argmax + two masked sums instead of a Python loop over Q).
+    The reference pairs the names ["Intra-video", "Inter-video"] with the SORTED unique type ids -- so with a single
+    type present it is reported as "Intra-video" whatever its id -- and that pairing is kept."""
+    preds, labels, types = torch.as_tensor(preds), torch.as_tensor(labels), torch.as_tensor(types)
+    hit = torch.argmax(preds, dim=1).to(labels.device) == labels.reshape(-1)
     metrics = {}
-    type_list = torch.unique(types)
-    group_list = ["Intra-video", "Inter-video"]
-    for type_i, group_i in zip(type_list, group_list):
-        correct = total = 0
-        for pred, label, typ in zip(preds, labels, types):
-            if typ == type_i:
-                pred_ = torch.argmax(pred)
-                if pred_.item() == label.item():
-                    correct += 1
-                total += 1
-        metrics[group_i] = correct / total * 100
+    for type_i, group_i in zip(torch.unique(types), ("Intra-video", "Inter-video")):
+        sel = types.reshape(-1) == type_i
+        metrics[group_i] = (hit & sel.to(hit.device)).sum().item() / sel.sum().item() * 100
     return metrics
 
 

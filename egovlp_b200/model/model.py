@@ -115,8 +115,10 @@ class FrozenInTime(BaseModel):
     def forward(self, data, video_only=False, return_embeds=True):
         if video_only:
             return self.compute_video(data['video'])
-        text_embeddings = self.compute_text(data['text'])
-        video_embeddings = self.compute_video(data['video'])
+        if torch.is_grad_enabled():
+            self._bf16_cache.refresh()           # once per training forward (both towers share the cache)
+        text_embeddings = self._text(data['text'], False, _refresh=False)
+        video_embeddings = self.compute_video(data['video'], _refresh=False)
         if return_embeds:
             return text_embeddings, video_embeddings
         return sim_matrix(text_embeddings, video_embeddings)
@@ -134,16 +136,18 @@ class FrozenInTime(BaseModel):
                   f.lin2.bias, layer.output_layer_norm.weight, layer.output_layer_norm.bias]
         return p
 
-    def _text(self, text_data, tokens_mode):
-        if not isinstance(self.txt_proj, nn.Sequential):
-            raise NotImplementedError("projection='' is not implemented for the text tower")
-        proj = self.txt_proj[1]
+    def _text(self, text_data, tokens_mode, _refresh=True):
+        # projection='' (nn.Identity, reference :80-82): the tower ends at the DistilBERT hidden state (no ReLU / Linear)
+        proj = self.txt_proj[1] if isinstance(self.txt_proj, nn.Sequential) else None
         cfg = self.text_model.config
+        if _refresh and torch.is_grad_enabled():
+            self._bf16_cache.refresh()
         # train-mode dropouts of the HF text model (the reference keeps `text_model.train()`, :36); eval() or a config
         # with dropout = attention_dropout = 0 gives the deterministic path
         drop = (cfg.dropout, cfg.attention_dropout) if self.text_model.training else (0.0, 0.0)
         return engine.TextTowerFn.apply(text_data['input_ids'], text_data['attention_mask'], cfg.n_heads, 1e-12,
-                                        tokens_mode, self._bf16_cache, drop, *self._text_params(), proj.weight, proj.bias)
+                                        (tokens_mode, torch.is_grad_enabled()), self._bf16_cache, drop, *self._text_params(),
+                                        *((proj.weight, proj.bias) if proj is not None else (None, None)))
 
     def compute_text(self, text_data):
         return self._text(text_data, False)
@@ -152,9 +156,9 @@ class FrozenInTime(BaseModel):
         return self._text(text_data, True)
 
     # ---- video -----------------------------------------------------------------------------------------------
-    def compute_video(self, video_data):
+    def compute_video(self, video_data, _refresh=True):
         proj = self.vid_proj[0] if isinstance(self.vid_proj, nn.Sequential) else None
-        return self.video_model.forward_features(video_data, proj=proj)
+        return self.video_model.forward_features(video_data, proj=proj, _refresh=_refresh)
 
     # ---- checkpoint compat -----------------------------------------------------------------------------------
     def _inflate_positional_embeds(self, new_state_dict):

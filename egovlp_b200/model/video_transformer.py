@@ -93,7 +93,7 @@ class SpaceTimeBlock(nn.Module):
         B = x.shape[0]
         eps = self.norm1.eps
         cache = cache if cache is not None else _default_cache(self)
-        return engine.SpaceTimeBlockFn.apply(x, (B, space_f, time_n, self.num_heads), eps, cache,
+        return engine.SpaceTimeBlockFn.apply(x, (B, space_f, time_n, self.num_heads, torch.is_grad_enabled()), eps, cache,
                                              *self.kernel_params())
 
 
@@ -152,11 +152,13 @@ class SpaceTimeTransformer(nn.Module):
         self.einops_from_time, self.einops_to_time = 'b (f n) d', '(b n) f d'
         object.__setattr__(self, "_bf16_cache", engine.Bf16Cache())
 
-    def forward_tokens(self, x):
+    def forward_tokens(self, x, _refresh=True):
         """All tokens after the 12 blocks, [B, S, D] fp32 (before the final norm)."""
         B, F, C, H, W = x.shape
         assert F <= self.num_frames
         cache = self._bf16_cache
+        if _refresh and torch.is_grad_enabled():
+            cache.refresh()                            # training forward: bf16 weight copies follow ANY optimizer
         pe = self.patch_embed
         # uint8 frames are normalised on the fly with `input_norm` = (mean, std) (default: ImageNet, as the reference's
         # data_loader/transforms.py); float frames are taken as already normalised (the reference contract).
@@ -167,9 +169,9 @@ class SpaceTimeTransformer(nn.Module):
             x = blk(x, time_n=n, space_f=F, cache=cache)
         return x
 
-    def forward_features(self, x, proj=None):
+    def forward_features(self, x, proj=None, _refresh=True):
         """norm(x)[:, 0]; when `proj` (an nn.Linear) is given its projection is fused behind the CLS LayerNorm."""
-        x = self.forward_tokens(x)
+        x = self.forward_tokens(x, _refresh)
         pw, pb = (proj.weight, proj.bias) if proj is not None else (None, None)
         return engine.ClsHeadFn.apply(x, self.norm.eps, self._bf16_cache, self.norm.weight, self.norm.bias, pw, pb)
 

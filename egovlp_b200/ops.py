@@ -128,6 +128,33 @@ def cast_bf16(src, dst=None):
     return dst
 
 
+class _CastDesc(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("numel", C.c_longlong)]
+
+
+def build_cast_table(pairs):
+    """Device-side descriptor / chunk tables for `cast_multi`: pairs = [(fp32 src, bf16 dst), ...] (contiguous)."""
+    chunk = lib().egovlp_adamw_chunk_elems()
+    descs = (_CastDesc * len(pairs))()
+    ct, co = [], []
+    for i, (src, dst) in enumerate(pairs):
+        _chk(src, F32, "src"); _chk(dst, BF16, "dst")
+        assert src.is_contiguous() and dst.is_contiguous() and src.numel() == dst.numel()
+        descs[i] = _CastDesc(src.data_ptr(), dst.data_ptr(), src.numel())
+        n = (src.numel() + chunk - 1) // chunk
+        ct += [i] * n
+        co += list(range(n))
+    dev = pairs[0][0].device
+    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).to(dev)
+    return raw, torch.tensor(ct, dtype=torch.int32, device=dev), torch.tensor(co, dtype=torch.int32, device=dev)
+
+
+def cast_multi(raw, chunk_tensor, chunk_offset):
+    """fp32 -> bf16 for every (src, dst) pair of a table from `build_cast_table`, one launch."""
+    call("egovlp_cast_multi_f32_to_bf16", _ptr(raw), _ptr(chunk_tensor), _ptr(chunk_offset), chunk_tensor.numel(),
+         _stream())
+
+
 def colsum_accum(dy, out):
     """out[n] += sum_m dy[m,n]; dy bf16/fp32 [M,N]."""
     assert dy.dim() == 2 and dy.stride(1) == 1 and out.dtype == F32 and out.numel() == dy.shape[1]
@@ -273,10 +300,14 @@ def positives_mask_from_tags(verb, noun, mode):
     return mask
 
 
-def positives_mask_from_sims(sim_v, sim_n, G, mode):
-    dev = (sim_v if sim_v is not None else sim_n).device if (sim_v is not None or sim_n is not None) else "cuda"
+def positives_mask_from_sims(sim_v, sim_n, G, mode, device=None):
+    """uint8 [G,G] positives mask; mode 0 (identity) needs `device` since it has no input tensor to take it from."""
+    src = sim_v if sim_v is not None else sim_n
+    dev = src.device if src is not None else torch.device(device)
+    assert dev.type == "cuda", f"positives mask: CUDA tensors expected, got {dev} (there is no CPU path)"
     mask = torch.empty(G, G, dtype=torch.uint8, device=dev)
-    call("egovlp_mask_from_sims", _ptr(sim_v), _ptr(sim_n), _ptr(mask), G, mode, _stream())
+    with torch.cuda.device(dev):
+        call("egovlp_mask_from_sims", _ptr(sim_v), _ptr(sim_n), _ptr(mask), G, mode, _stream())
     return mask
 
 

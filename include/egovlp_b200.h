@@ -228,11 +228,25 @@ typedef struct egovlp_adamw_tensor {
   float* exp_avg;
   float* exp_avg_sq;
   long long numel;
+  void* shadow_bf16;   /* optional: bf16 copy of the updated parameter written in the same pass (NULL: none) */
 } egovlp_adamw_tensor;
 int egovlp_adamw_chunk_elems(void);
 int egovlp_adamw_multi(const egovlp_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_offset_dev,
                        int n_chunks, float lr, float beta1, float beta2, float eps, float weight_decay, float step_size,
                        const float* grad_scale_dev, void* stream);
+
+
+/* fp32 -> bf16 cast of many tensors in ONE launch (the bf16 GEMM-operand copies of all fp32 master weights, refreshed at
+ * the top of every training forward so that ANY optimizer -- e.g. transformers.AdamW updating through p.data, as
+ * run/train_egoclip.py:72-73 configures -- is seen).  Same chunk-table scheme as egovlp_adamw_multi
+ * (egovlp_adamw_chunk_elems() elements per chunk). */
+typedef struct egovlp_cast_tensor {
+  const float* src;
+  void* dst_bf16;
+  long long numel;
+} egovlp_cast_tensor;
+int egovlp_cast_multi_f32_to_bf16(const egovlp_cast_tensor* tensors_dev, const int* chunk_tensor_dev,
+                                  const int* chunk_offset_dev, int n_chunks, void* stream);
 
 #ifdef __cplusplus
 }
