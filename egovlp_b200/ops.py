@@ -21,19 +21,46 @@ def _chk(t, dtype, name):
     assert t.is_cuda and t.dtype == dtype, f"{name}: expected cuda {dtype}, got {t.device} {t.dtype}"
 
 
-_gemm_prof = None
+_prof = None         # bench.py's live roofline probe: {kind: [(work, start event, end event), ...]}
+
+
+def profile(enable):
+    """CUDA events (on the launching stream) around every GEMM / divided-attention / LayerNorm launch.
+    profile(True) starts recording; profile(False) returns {kind: (work, milliseconds, launches)} where `work` is the
+    algorithmic FLOPs (kind 'gemm') or algorithmic HBM bytes (the HBM-bound kinds) of the recorded launches."""
+    global _prof
+    if enable:
+        _prof = {}
+        return None
+    rec, _prof = _prof or {}, None
+    torch.cuda.synchronize()
+    return {k: (sum(r[0] for r in v), sum(r[1].elapsed_time(r[2]) for r in v), len(v)) for k, v in rec.items()}
 
 
 def profile_gemm(enable):
-    """bench.py's live roofline probe: CUDA events (on the launching stream) around every tcgen05 GEMM launch.
-    profile_gemm(True) starts recording; profile_gemm(False) returns (flops, milliseconds, launches)."""
-    global _gemm_prof
-    if enable:
-        _gemm_prof = []
-        return None
-    rec, _gemm_prof = _gemm_prof or [], None
-    torch.cuda.synchronize()
-    return sum(r[0] for r in rec), sum(r[1].elapsed_time(r[2]) for r in rec), len(rec)
+    """GEMM-only view of `profile` (tools/): profile_gemm(False) -> (flops, milliseconds, launches)."""
+    res = profile(enable)
+    return None if enable else res.get("gemm", (0.0, 0.0, 0))
+
+
+class _Probe:
+    """`with _Probe(kind, work):` records one launch when profiling is on (no-op otherwise)."""
+    __slots__ = ("kind", "work", "e0")
+
+    def __init__(self, kind, work):
+        self.kind, self.work, self.e0 = kind, work, None
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _prof.setdefault(self.kind, []).append((self.work, self.e0, e1))
+        return False
 
 
 def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=None, out2=None, act=0, alpha=1.0,
@@ -78,14 +105,9 @@ def gemm(a, b, out, *, a_mn=False, b_mn=False, bias=None, residual=None, aux=Non
     if colsum_a is not None:                 # wgrad form only: column sums of A accumulated from the smem tiles
         _chk(colsum_a, F32, "colsum_a"); assert a_mn and b_mn and colsum_a.numel() == M
     e.colsum_a = colsum_a.data_ptr() if colsum_a is not None else None
-    if _gemm_prof is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-    call("egovlp_gemm_bf16", _ptr(a), int(a_mn), C.c_longlong(a.stride(0)), _ptr(b), int(b_mn),
-         C.c_longlong(b.stride(0)), M, N, K, C.byref(e), split_k, _stream())
-    if _gemm_prof is not None:
-        e1.record()
-        _gemm_prof.append((2.0 * M * N * K, e0, e1))
+    with _Probe("gemm", 2.0 * M * N * K):
+        call("egovlp_gemm_bf16", _ptr(a), int(a_mn), C.c_longlong(a.stride(0)), _ptr(b), int(b_mn),
+             C.c_longlong(b.stride(0)), M, N, K, C.byref(e), split_k, _stream())
     return out
 
 
@@ -97,8 +119,10 @@ def layernorm_fwd(x, gamma, beta, eps, *, add=None, sum_out=None, y16=None, y32=
     for t in (add, sum_out, y32):
         assert t is None or (t.dtype == F32 and t.is_contiguous() and t.shape == (rows, D))
     assert y16 is None or (y16.dtype == BF16 and y16.is_contiguous() and y16.shape == (rows, D))
-    call("egovlp_layernorm_fwd", _ptr(x), C.c_longlong(x.stride(0)), _ptr(add), _ptr(sum_out), _ptr(gamma),
-         _ptr(beta), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), rows, D, C.c_float(eps), _stream())
+    nbytes = rows * D * (4 + 4 * (add is not None) + 4 * (sum_out is not None) + 2 * (y16 is not None) + 4 * (y32 is not None))
+    with _Probe("layernorm_fwd", nbytes):
+        call("egovlp_layernorm_fwd", _ptr(x), C.c_longlong(x.stride(0)), _ptr(add), _ptr(sum_out), _ptr(gamma),
+             _ptr(beta), _ptr(y16), _ptr(y32), _ptr(mean), _ptr(rstd), rows, D, C.c_float(eps), _stream())
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx16=None, dgamma=None, dbeta=None,
@@ -111,12 +135,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, *, add1=None, add2=None, dx=None, dx
         assert t is None or (t.dtype in (F32, BF16) and t.is_contiguous() and t.shape == (rows, D))
     assert dx is None or (dx.dtype == F32 and dx.shape == (rows, D) and dx.stride(1) == 1)
     assert dx16 is None or (dx16.dtype == BF16 and dx16.is_contiguous() and dx16.shape == (rows, D))
-    call("egovlp_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), C.c_longlong(dy.stride(0)), _ptr(x),
-         C.c_longlong(x.stride(0)), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1),
-         int(add1 is not None and add1.dtype == BF16), _ptr(add2), int(add2 is not None and add2.dtype == BF16),
-         _ptr(dx), C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
-         _ptr(colsum_dx), rows, D,
-         _stream())
+    nbytes = rows * D * (dy.element_size() + 4 + sum(t.element_size() for t in (add1, add2) if t is not None)
+                         + 4 * (dx is not None) + 2 * (dx16 is not None))
+    with _Probe("layernorm_bwd", nbytes):
+        call("egovlp_layernorm_bwd", _ptr(dy), int(dy.dtype == BF16), C.c_longlong(dy.stride(0)), _ptr(x),
+             C.c_longlong(x.stride(0)), _ptr(gamma), _ptr(mean), _ptr(rstd), _ptr(add1),
+             int(add1 is not None and add1.dtype == BF16), _ptr(add2), int(add2 is not None and add2.dtype == BF16),
+             _ptr(dx), C.c_longlong(dx.stride(0) if dx is not None else D), _ptr(dx16), _ptr(dgamma), _ptr(dbeta),
+             _ptr(colsum_dx), rows, D, _stream())
 
 
 def cast_bf16(src, dst=None):
@@ -172,7 +198,9 @@ def divided_attn_fwd(qkv, B, T, N, H, mode):
     n_ws = lib().egovlp_divided_attn_workspace_floats(B, T, N, H, mode)
     assert n_ws > 0, "unsupported attention geometry"
     ws = torch.empty(n_ws, dtype=F32, device=qkv.device)
-    call("egovlp_divided_attn_fwd", _ptr(qkv), _ptr(out), _ptr(lse), _ptr(ws), B, T, N, H, mode, _stream())
+    # algorithmic bytes: read q|k|v once (3 x 2 D), write the output (2 D) and the lse (4 H) per token
+    with _Probe("attn_time_fwd" if mode == 0 else "attn_space_fwd", B * S * (8 * D + 4 * H)):
+        call("egovlp_divided_attn_fwd", _ptr(qkv), _ptr(out), _ptr(lse), _ptr(ws), B, T, N, H, mode, _stream())
     return out, lse
 
 
@@ -182,8 +210,11 @@ def divided_attn_bwd(qkv, out, dout, lse, B, T, N, H, mode, q_scale, dqkv=None):
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     ws = torch.empty(B * H * 3 * 64, dtype=F32, device=qkv.device)
-    call("egovlp_divided_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(ws), B, T, N, H,
-         mode, C.c_float(q_scale), _stream())
+    S, D = 1 + T * N, 64 * H
+    # algorithmic bytes: read q|k|v, out, dout and the lse once, write dq|dk|dv
+    with _Probe("attn_time_bwd" if mode == 0 else "attn_space_bwd", B * S * (16 * D + 4 * H)):
+        call("egovlp_divided_attn_bwd", _ptr(qkv), _ptr(out), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(ws), B, T, N, H,
+             mode, C.c_float(q_scale), _stream())
     return dqkv
 
 

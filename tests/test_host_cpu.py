@@ -165,8 +165,10 @@ def test_bench_flop_model_matches_the_survey_and_the_oracle_counter():
     assert abs(video / 1e9 - 739.177) < 0.01 and abs(text / 1e9 - 1.364) < 0.01 and abs(step / 1e9 - 2217.9) < 0.1
     step4, video4, _ = bench.flops_per_clip(4, 16)
     assert abs(video4 / 1e9 - 184.617) < 0.01 and abs(step4 / 1e9 - 557.0) < 0.1
-    cfg = bench.workload_config(type("A", (), {"frames": 16, "text_len": 16, "batch": 64})(), 8)
-    assert cfg["global_batch"] == 512 and cfg["parallelism"] == "dp8" and "workload" in cfg
+    a = type("A", (), {"frames": 16, "text_len": 16, "batch": 64, "workload": "cfg3"})()
+    cfg = bench.workload_config(a, bench.WORKLOADS["cfg3"], 8)
+    assert cfg["global_batch"] == 512 and cfg["parallelism"] == "dp8" and cfg["workload"].startswith("cfg3")
+    assert set(bench.WORKLOADS) == {"cfg2", "cfg3", "cfg4", "cfg5"}
     # forward FLOPs of the tiny tower, counted by torch on the oracle, against the same formula
     from torch.utils.flop_counter import FlopCounterMode
     from oracle import reference_port as rp
