@@ -23,6 +23,10 @@ namespace egovlp {
 
 // tcgen05 / TMEM space-attention forward (attention_tc.cu)
 bool space_attn_tc_supported(int N);
+// tcgen05 / TMEM space-attention backward (attention_tc_bwd.cu)
+bool space_attn_bwd_tc_supported(int N);
+int space_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dcls,
+                      int B, int T, int N, int H, float q_scale, cudaStream_t st);
 int space_attn_fwd_tc(const void* qkv, void* out, float* lse, float* cls_part, int B, int T, int N, int H,
                       cudaStream_t st);
 
@@ -1287,7 +1291,10 @@ extern "C" int egovlp_divided_attn_bwd(const void* qkv, const void* out, const v
     KERN<<<grid, W * 32, smem, st>>>(tmq, tmd, q, o, d_o, lse, dq, dcls_ws, q_scale, G, ##__VA_ARGS__);       \
   } while (0)
   const bool generic = force_generic() || (mode == 0 && !time_fast_ok(G));
-  if (generic) {
+  if (!generic && mode == 1 && space_attn_bwd_tc_supported(N)) {     // tcgen05 / TMEM kernel (default at N = 196)
+    rc = space_attn_bwd_tc(qkv, out, dout, lse, dqkv, dcls_ws, B, T, N, H, q_scale, st);
+    if (rc) return rc;
+  } else if (generic) {
     if (G.NPAD > 128) LAUNCH_BWD((divided_attn_bwd_kernel<7, 2>), 7);
     else LAUNCH_BWD((divided_attn_bwd_kernel<4, 3>), 4);
   } else if (mode == 1) {     // space: 2 CTAs / SM (4 x 26 KB tiles each, no staging)

@@ -1,0 +1,519 @@
+// Space attention BACKWARD on tcgen05 / TMEM (the N-length attention of VarAttention in '(b f) n d' mode,
+// model/video_transformer.py:109-133, differentiated): all five contractions of a (b, head, frame) group
+//     S = Q K^T     dP = dO V^T     dV = P^T dO     dK = dS^T Q     dQ = dS K          (P = exp(S - lse), dS = P o (dP - delta))
+// are UMMA tiles with TMEM accumulators; Q / K / V / dO arrive by TMA, P and dS go through 128B-swizzled shared memory
+// ONCE and serve three operand roles (the same bytes are a K-major A tile for dQ and an MN-major A tile for dV / dK), so
+// every contraction is computed exactly once per group -- the mma.sync kernel in attention.cu recomputes S and dP in
+// both of its phases (7 GEMM units instead of 5).  Same inputs / outputs / CLS semantics as fast_attn_bwd_kernel<false>.
+//
+// Group rows: 0..N-1 = the frame's patches, row N = the CLS token (as a key for every patch query; as a query it sees the
+// patch keys of the frame and, in frame 0 only, the CLS key -- its lse / delta are the global ones), rows N+1..NKP-1
+// zero padding.  One persistent CTA per SM loops over groups, each in four (key tile kt, query tile qt) steps of a
+// 128 x 128 block (second tiles are 128 x (NKP-128)):
+//   warp 0     TMA producer: a ring of 6 tile slots [NKP rows x 128 B]; Q, K, dO, V of a group (patch rows + the CLS row
+//              box each), so the next group's Q / K are in flight while this one computes
+//   warp 1     MMA issuer (one thread): S and dP of the next step are issued as soon as the softmax warps have pulled the
+//              current ones out of TMEM; dV after P is in smem, dK / dQ after dS
+//   warp 2     TMEM allocator: 512 columns = S 128 | dP 128 | dQ_0 64 | dQ_1 64 | dK 64 | dV 64
+//   warps 4-11 two threads per query row (64 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) -> smem,
+//              dS = P (dP - delta) -> smem, and the accumulator drains (dK / dV per key tile, dQ per group) straight to
+//              dqkv as 64-byte row pieces; CLS-row gradients by fp32 atomics.  delta = rowsum(dO o O) is computed per group
+//              from O rows prefetched during the previous group's drain.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "egovlp_b200.h"
+
+namespace egovlp {
+namespace {
+
+constexpr int HD = 64;
+constexpr int ROWB = 128;                  // bytes per head row
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr int TILE_ROWS = 208;
+constexpr int TILE_BYTES = TILE_ROWS * ROWB;          // 26 KB, 1024-aligned
+constexpr int NSLOT = 6;
+constexpr int PB_BYTES = 2 * 128 * ROWB;              // [2 key blocks of 64][128 query rows][128 B]
+constexpr int KBLK_BYTES = 128 * ROWB;                // one 64-key block
+constexpr int LSD_FLOATS = 2 * 2 * TILE_ROWS;         // [parity][lse2 | delta][row]
+constexpr int THREADS = 384;
+constexpr int S_COL = 0, DP_COL = 128, DQ_COL = 256, DK_COL = 384, DV_COL = 448;
+
+struct BwdGeom {
+  int B, H, T, N, S, D, NK, NKP, W1, groups;        // W1 = NKP - 128: width of the second key / query tile
+};
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(r));
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// arrive (one per warp) after this warp's TMEM reads / generic-proxy smem writes are complete
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// 32 fp32 accumulator values of one row -> 64 contiguous bytes of bf16
+__device__ __forceinline__ void store_row32(const uint32_t (&v)[32], float scale, bf16* dst) {
+  uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    d[c] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * c]) * scale, __uint_as_float(v[8 * c + 1]) * scale),
+                      pack_bf16x2(__uint_as_float(v[8 * c + 2]) * scale, __uint_as_float(v[8 * c + 3]) * scale),
+                      pack_bf16x2(__uint_as_float(v[8 * c + 4]) * scale, __uint_as_float(v[8 * c + 5]) * scale),
+                      pack_bf16x2(__uint_as_float(v[8 * c + 6]) * scale, __uint_as_float(v[8 * c + 7]) * scale));
+}
+__device__ __forceinline__ void atomic_row32(const uint32_t (&v)[32], float* dst) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_cls,
+                         const __grid_constant__ CUtensorMap tm_do_rows, const __grid_constant__ CUtensorMap tm_do_cls,
+                         const bf16* __restrict__ out, const float* __restrict__ lse_in, bf16* __restrict__ dqkv,
+                         float* __restrict__ dcls, float q_scale, BwdGeom G) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sP = base + NSLOT * TILE_BYTES;
+  const uint32_t sDS = sP + PB_BYTES;
+  const uint32_t lsd_off = NSLOT * TILE_BYTES + 2 * PB_BYTES;
+  float* lsd = reinterpret_cast<float*>(gen + lsd_off);
+  const uint32_t bars = base + lsd_off + LSD_FLOATS * 4;
+  const uint32_t tile_full = bars, tile_empty = bars + 48;
+  const uint32_t s_full = bars + 96, s_free = bars + 104, dp_full = bars + 112, dp_free = bars + 120;
+  const uint32_t p_ready = bars + 128, p_freeb = bars + 136, ds_ready = bars + 144, ds_freeb = bars + 152;
+  const uint32_t dkv_full = bars + 160, dkv_free = bars + 168, dq_full = bars + 176, dq_free = bars + 184;
+  const uint32_t tmem_slot = bars + 192;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // zero the padding rows NK .. TILE_ROWS-1 of every slot once (TMA never writes them): they enter dV / dK / dQ as
+  // contraction rows with zero P / dS and must therefore be finite
+  for (int i = threadIdx.x; i < NSLOT * (TILE_ROWS - G.NK) * 8; i += THREADS) {
+    const int c = i & 7, rr = (i >> 3) % (TILE_ROWS - G.NK), slot = (i >> 3) / (TILE_ROWS - G.NK);
+    *reinterpret_cast<uint4*>(gen + slot * TILE_BYTES + (G.NK + rr) * ROWB + c * 16) = make_uint4(0, 0, 0, 0);
+  }
+  // P / dS start as zeros: their never-written corners are read as garbage ROWS / lanes only, but keep them finite
+  for (int i = threadIdx.x; i < 2 * PB_BYTES / 16; i += THREADS)
+    *reinterpret_cast<uint4*>(gen + NSLOT * TILE_BYTES + i * 16) = make_uint4(0, 0, 0, 0);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_rows); tma_prefetch_desc(&tm_cls);
+    tma_prefetch_desc(&tm_do_rows); tma_prefetch_desc(&tm_do_cls);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < NSLOT; ++i) { mbar_init(tile_full + 8 * i, 1); mbar_init(tile_empty + 8 * i, 1); }
+    mbar_init(s_full, 1);   mbar_init(s_free, 8);
+    mbar_init(dp_full, 1);  mbar_init(dp_free, 8);
+    mbar_init(p_ready, 8);  mbar_init(p_freeb, 1);
+    mbar_init(ds_ready, 8); mbar_init(ds_freeb, 1);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);
+    mbar_init(dq_full, 1);  mbar_init(dq_free, 8);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const int ksteps1 = G.W1 / 16;                        // contraction steps over the second (short) tile
+
+  // register budget: the three single-thread roles give registers back, the softmax warps take them (168 -> 216, 72 for the others)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int gi = 0;
+      for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
+        const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {                    // Q, K, dO, V
+          const int c = 4 * gi + j, slot = c % NSLOT, u = c / NSLOT;
+          mbar_wait(tile_empty + 8 * slot, (u & 1) ^ 1);
+          const uint32_t fb = tile_full + 8 * slot, dst = base + slot * TILE_BYTES;
+          mbar_expect_tx(fb, (uint32_t)G.NK * ROWB);
+          if (j == 2) {
+            tma_load_4d(dst, &tm_do_rows, fb, 0, 1 + f * G.N, h, b);
+            tma_load_4d(dst + G.N * ROWB, &tm_do_cls, fb, 0, 0, h, b);
+          } else {
+            const int w = j == 0 ? 0 : (j == 1 ? 1 : 2);
+            tma_load_4d(dst, &tm_rows, fb, 0, 1 + f * G.N, w * G.H + h, b);
+            tma_load_4d(dst + G.N * ROWB, &tm_cls, fb, 0, 0, w * G.H + h, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    const uint32_t idesc_s0 = make_idesc_bf16(128, 128, false, false);
+    const uint32_t idesc_s1 = make_idesc_bf16(128, G.W1, false, false);
+    constexpr uint32_t idesc_kv = make_idesc_bf16(128, HD, true, true);      // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
+    constexpr uint32_t idesc_q = make_idesc_bf16(128, HD, false, true);      // A = dS (K-major), B = K (MN-major)
+    int gi = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
+      const int c0 = 4 * gi;
+      const uint32_t tq = base + ((c0 + 0) % NSLOT) * TILE_BYTES, tk = base + ((c0 + 1) % NSLOT) * TILE_BYTES;
+      const uint32_t tdo = base + ((c0 + 2) % NSLOT) * TILE_BYTES, tv = base + ((c0 + 3) % NSLOT) * TILE_BYTES;
+
+      auto issue_s = [&](int it) {                       // S[qt rows, kt keys] = Q K^T
+        const int kt = it >> 1, qt = it & 1;
+        if (lane == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem + S_COL, make_smem_desc_sw128(tq + qt * 128 * ROWB + kk * 32, 16, 1024),
+                         make_smem_desc_sw128(tk + kt * 128 * ROWB + kk * 32, 16, 1024), kt ? idesc_s1 : idesc_s0, kk > 0);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+      };
+      auto issue_dp = [&](int it) {                      // dP = dO V^T
+        const int kt = it >> 1, qt = it & 1;
+        if (lane == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16_ss(tmem + DP_COL, make_smem_desc_sw128(tdo + qt * 128 * ROWB + kk * 32, 16, 1024),
+                         make_smem_desc_sw128(tv + kt * 128 * ROWB + kk * 32, 16, 1024), kt ? idesc_s1 : idesc_s0, kk > 0);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
+      };
+
+      // first step of the group: S needs Q, K; dP needs dO, V
+      {
+        const int n = 4 * gi;
+        mbar_wait(tile_full + 8 * ((c0 + 0) % NSLOT), ((c0 + 0) / NSLOT) & 1);
+        mbar_wait(tile_full + 8 * ((c0 + 1) % NSLOT), ((c0 + 1) / NSLOT) & 1);
+        mbar_wait(s_free, (n & 1) ^ 1);
+        tc_fence_after();
+        issue_s(0);
+        mbar_wait(tile_full + 8 * ((c0 + 2) % NSLOT), ((c0 + 2) / NSLOT) & 1);
+        mbar_wait(tile_full + 8 * ((c0 + 3) % NSLOT), ((c0 + 3) / NSLOT) & 1);
+        mbar_wait(dp_free, (n & 1) ^ 1);
+        tc_fence_after();
+        issue_dp(0);
+      }
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        const int n = 4 * gi + it, kt = it >> 1, qt = it & 1;
+        const int ks_q = qt ? ksteps1 : 8;               // contraction over this query tile's rows
+        const int ks_k = kt ? ksteps1 : 8;               // contraction over this key tile's rows
+        // ---- dV[kt] (+)= P^T dO
+        mbar_wait(p_ready, n & 1);
+        if (qt == 0) mbar_wait(dkv_free, ((2 * gi + kt) & 1) ^ 1);       // previous key tile's dK / dV drained
+        tc_fence_after();
+        if (lane == 0) {
+          for (int j = 0; j < ks_q; ++j)
+            umma_bf16_ss(tmem + DV_COL, make_smem_desc_sw128(sP + j * 2048, KBLK_BYTES, 1024),
+                         make_smem_desc_sw128(tdo + (qt * 128 + j * 16) * ROWB, 8192, 1024), idesc_kv, (qt | j) != 0);
+          umma_commit(p_freeb);
+        }
+        __syncwarp();
+        // ---- S of the next step as soon as the current S has left TMEM
+        if (it < 3) {
+          mbar_wait(s_free, ((n + 1) & 1) ^ 1);
+          tc_fence_after();
+          issue_s(it + 1);
+        }
+        // ---- dK[kt] (+)= dS^T Q,  dQ[qt] (+)= dS K
+        mbar_wait(ds_ready, n & 1);
+        if (it == 0) mbar_wait(dq_free, (gi & 1) ^ 1);                   // previous group's dQ drained
+        tc_fence_after();
+        if (lane == 0) {
+          for (int j = 0; j < ks_q; ++j)
+            umma_bf16_ss(tmem + DK_COL, make_smem_desc_sw128(sDS + j * 2048, KBLK_BYTES, 1024),
+                         make_smem_desc_sw128(tq + (qt * 128 + j * 16) * ROWB, 8192, 1024), idesc_kv, (qt | j) != 0);
+          for (int j = 0; j < ks_k; ++j)
+            umma_bf16_ss(tmem + DQ_COL + 64 * qt, make_smem_desc_sw128(sDS + (j >> 2) * KBLK_BYTES + (j & 3) * 32, 16, 1024),
+                         make_smem_desc_sw128(tk + (kt * 128 + j * 16) * ROWB, 8192, 1024), idesc_q, (kt | j) != 0);
+          umma_commit(ds_freeb);
+          if (qt == 1) umma_commit(dkv_full);
+          if (it == 3) {
+            umma_commit(dq_full);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) umma_commit(tile_empty + 8 * ((c0 + j) % NSLOT));
+          }
+        }
+        __syncwarp();
+        if (it < 3) {
+          mbar_wait(dp_free, ((n + 1) & 1) ^ 1);
+          tc_fence_after();
+          issue_dp(it + 1);
+        }
+      }
+    }
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ============================== softmax / dS / drains ==============================
+    const int qd = warp & 3, hf = (warp - 4) >> 2;
+    const int r_in = qd * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const int tid_c = threadIdx.x - 128;                 // 0..255: the row this thread prepares (lse, delta)
+    const int half1 = ((G.W1 / 8 + 1) / 2) * 8;          // columns of half 0 in the short key tile (multiple of 8)
+
+    // O row + lse of row tid_c of group g: pulled into L2 one group ahead (no registers held across the group), read at
+    // the top of the group
+    auto row_ptrs = [&](int g, const uint4*& orow, const float*& lrow) {
+      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+      const int tok = tid_c < G.N ? 1 + f * G.N + tid_c : 0;
+      orow = reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD);
+      lrow = lse_in + ((long long)(b * G.H + h)) * G.S + tok;
+    };
+    auto prefetch_rows = [&](int g) {
+      if (g < G.groups && tid_c < G.NK) {
+        const uint4* orow; const float* lrow;
+        row_ptrs(g, orow, lrow);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(orow));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(lrow));
+      }
+    };
+    prefetch_rows(blockIdx.x);
+
+    int gi = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
+      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+      const int c0 = 4 * gi;
+      float* lse2_s = lsd + (gi & 1) * 2 * TILE_ROWS;
+      float* delta_s = lse2_s + TILE_ROWS;
+      // ---- per-row lse (log2 units) and delta = rowsum(dO o O)
+      {
+        const uint32_t slot = (c0 + 2) % NSLOT;
+        uint4 o_pre[8];
+        float lse_pre = 0.f;
+        if (tid_c < G.NK) {
+          const uint4* orow; const float* lrow;
+          row_ptrs(g, orow, lrow);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o_pre[i] = __ldg(orow + i);
+          lse_pre = __ldg(lrow);
+        }
+        mbar_wait(tile_full + 8 * slot, ((c0 + 2) / NSLOT) & 1);
+        if (tid_c < G.NK) {
+          const uint8_t* dorow = gen + slot * TILE_BYTES + tid_c * ROWB;
+          float d = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const uint4 dv = *reinterpret_cast<const uint4*>(dorow + ((cc ^ (tid_c & 7)) << 4));
+            const uint4 ov = o_pre[cc];
+            const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w}, ou[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = unpack_bf16x2(ou[i]), bb = unpack_bf16x2(du[i]);
+              d = fmaf(a.x, bb.x, d);
+              d = fmaf(a.y, bb.y, d);
+            }
+          }
+          lse2_s[tid_c] = lse_pre * LOG2E;
+          delta_s[tid_c] = d;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+
+#pragma unroll 1
+      for (int it = 0; it < 4; ++it) {
+        const int n = 4 * gi + it, kt = it >> 1, qt = it & 1;
+        const int row = qt * 128 + r_in;                 // query row of the group
+        const bool active = !(qt == 1 && qd * 32 >= G.W1);          // this warp's rows are beyond the padded tile
+        const bool rvalid = row < G.NK;
+        // keys this query may attend: all NK, except the CLS query outside frame 0 (no CLS key)
+        const int nvis = rvalid ? ((row == G.N && f != 0) ? G.N : G.NK) : 0;
+        const int ncol = kt ? (hf ? G.W1 - half1 : half1) : 64;     // this thread's columns of the key tile
+        const int col0 = kt ? hf * half1 : hf * 64;
+        const float lse2 = rvalid ? lse2_s[row] : 0.f, delta = rvalid ? delta_s[row] : 0.f;
+        uint32_t pk[32];                                 // P of this thread's columns, bf16 pairs (what dV consumes)
+
+        // ---- S -> P
+        mbar_wait(s_full, n & 1);
+        tc_fence_after();
+        {
+          uint32_t sv[64];
+          if (active) {
+            const uint32_t a = tmem + lane_base + S_COL + col0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (8 * c < ncol) tmem_ld8(a + 8 * c, sv + 8 * c);
+            tmem_ld_wait();
+          }
+          warp_arrive(s_free, lane);
+          if (active) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool ok0 = 2 * j < ncol && kt * 128 + col0 + 2 * j < nvis;
+              const bool ok1 = 2 * j + 1 < ncol && kt * 128 + col0 + 2 * j + 1 < nvis;
+              const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(sv[2 * j]), LOG2E, -lse2)) : 0.f;
+              const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(sv[2 * j + 1]), LOG2E, -lse2)) : 0.f;
+              pk[j] = pack_bf16x2(p0, p1);
+            }
+          }
+        }
+        mbar_wait(p_freeb, (n & 1) ^ 1);                 // the previous step's dV has consumed the P buffer
+        if (active) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (8 * c < ncol) {
+              const int col = col0 + 8 * c;
+              const uint32_t a = sP + (col >> 6) * KBLK_BYTES + r_in * ROWB + ((((col & 63) >> 3) ^ (r_in & 7)) << 4);
+              st_shared_v4(a, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();                        // generic-proxy stores -> visible to the UMMA reads
+        warp_arrive(p_ready, lane);
+
+        // ---- dP -> dS = P (dP - delta), 32 columns at a time
+        mbar_wait(dp_full, n & 1);
+        tc_fence_after();
+        mbar_wait(ds_freeb, (n & 1) ^ 1);                // the previous step's dK / dQ have consumed the dS buffer
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          if (active && 32 * hh < ncol) {
+            uint32_t dp[32];
+            const uint32_t a = tmem + lane_base + DP_COL + col0 + 32 * hh;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (32 * hh + 8 * c < ncol) tmem_ld8(a + 8 * c, dp + 8 * c);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (32 * hh + 8 * c < ncol) {
+                uint32_t dsp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const uint32_t pp = pk[16 * hh + 4 * c + j];
+                  const float p0 = __uint_as_float(pp << 16), p1 = __uint_as_float(pp & 0xffff0000u);
+                  // masked / padded elements have P == 0 exactly: their dP may be garbage (rows beyond the tile)
+                  const float d0 = p0 != 0.f ? p0 * (__uint_as_float(dp[8 * c + 2 * j]) - delta) : 0.f;
+                  const float d1 = p1 != 0.f ? p1 * (__uint_as_float(dp[8 * c + 2 * j + 1]) - delta) : 0.f;
+                  dsp[j] = pack_bf16x2(d0, d1);
+                }
+                const int col = col0 + 32 * hh + 8 * c;
+                const uint32_t sa = sDS + (col >> 6) * KBLK_BYTES + r_in * ROWB + ((((col & 63) >> 3) ^ (r_in & 7)) << 4);
+                st_shared_v4(sa, dsp[0], dsp[1], dsp[2], dsp[3]);
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        warp_arrive(dp_free, lane);
+        if (lane == 0) mbar_arrive(ds_ready);            // (ordered after the fences + __syncwarp of warp_arrive)
+
+        // ---- key tile complete: drain dK / dV rows (keys kt*128 + r_in), this thread's 32 of the 64 columns
+        if (qt == 1) {
+          mbar_wait(dkv_full, (2 * gi + kt) & 1);
+          tc_fence_after();
+          const int key = kt * 128 + r_in;
+          const bool any = !(kt == 1 && qd * 32 >= G.W1);
+          uint32_t dk[32], dv[32];
+          if (any) {
+            tmem_ld32(tmem + lane_base + DK_COL + hf * 32, dk);
+            tmem_ld32(tmem + lane_base + DV_COL + hf * 32, dv);
+            tmem_ld_wait();
+          }
+          warp_arrive(dkv_free, lane);
+          if (any && key < G.N) {
+            bf16* rowp = dqkv + ((long long)b * G.S + 1 + f * G.N + key) * (3 * G.D) + h * HD + hf * 32;
+            store_row32(dk, 1.f, rowp + G.D);
+            store_row32(dv, 1.f, rowp + 2 * G.D);
+          } else if (any && key == G.N) {                // the CLS key: summed over every group of (b, h)
+            atomic_row32(dk, dcls + ((long long)(b * G.H + h) * 3 + 1) * HD + hf * 32);
+            atomic_row32(dv, dcls + ((long long)(b * G.H + h) * 3 + 2) * HD + hf * 32);
+          }
+        }
+      }
+
+      // ---- next group's O rows / lse on their way while the dQ accumulators are drained
+      prefetch_rows(g + gridDim.x);
+      mbar_wait(dq_full, gi & 1);
+      tc_fence_after();
+      {
+        uint32_t dq0[32], dq1[32];
+        const bool any1 = qd * 32 < G.W1;
+        tmem_ld32(tmem + lane_base + DQ_COL + hf * 32, dq0);
+        if (any1) tmem_ld32(tmem + lane_base + DQ_COL + 64 + hf * 32, dq1);
+        tmem_ld_wait();
+        warp_arrive(dq_free, lane);
+        // the CLS query (row N): raw sum over the groups of (b, h), scaled by cls_grad_finalize_kernel
+        bf16* q0 = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD + hf * 32;
+        float* cls_q = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD + hf * 32;
+        if (r_in < G.N) store_row32(dq0, q_scale, q0 + (long long)r_in * (3 * G.D));
+        if (any1) {
+          const int row = 128 + r_in;
+          if (row < G.N) store_row32(dq1, q_scale, q0 + (long long)row * (3 * G.D));
+          else if (row == G.N) atomic_row32(dq1, cls_q);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+// Geometry the kernel covers: two key / query tiles, 128 < N + 1 <= 208.  EGOVLP_ATTN_TC_BWD=0 keeps the mma.sync kernel.
+bool space_attn_bwd_tc_supported(int N) {
+  const char* e = getenv("EGOVLP_ATTN_TC_BWD");
+  if (e && e[0] == '0') return false;
+  const int NK = N + 1;
+  return NK > 128 && NK <= TILE_ROWS;
+}
+
+int space_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, float* dcls,
+                      int B, int T, int N, int H, float q_scale, cudaStream_t st) {
+  BwdGeom G;
+  G.B = B; G.H = H; G.T = T; G.N = N; G.S = 1 + T * N; G.D = H * HD; G.NK = N + 1; G.NKP = (G.NK + 15) / 16 * 16;
+  G.W1 = G.NKP - 128; G.groups = B * H * T;
+  CUtensorMap tm_rows, tm_cls, tm_do_rows, tm_do_cls;
+  {
+    const uint64_t W = 3ull * G.D;
+    const uint64_t dims[4] = {HD, (uint64_t)G.S, (uint64_t)(3 * H), (uint64_t)B};
+    const uint64_t strides[4] = {1, W, HD, (uint64_t)G.S * W};
+    const uint32_t box_rows[4] = {HD, (uint32_t)N, 1, 1}, box_cls[4] = {HD, 1, 1, 1};
+    int rc = make_tmap_nd_bf16(&tm_rows, qkv, 4, dims, strides, box_rows, true);
+    if (rc) return rc;
+    rc = make_tmap_nd_bf16(&tm_cls, qkv, 4, dims, strides, box_cls, true);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t W = (uint64_t)G.D;
+    const uint64_t dims[4] = {HD, (uint64_t)G.S, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[4] = {1, W, HD, (uint64_t)G.S * W};
+    const uint32_t box_rows[4] = {HD, (uint32_t)N, 1, 1}, box_cls[4] = {HD, 1, 1, 1};
+    int rc = make_tmap_nd_bf16(&tm_do_rows, dout, 4, dims, strides, box_rows, true);
+    if (rc) return rc;
+    rc = make_tmap_nd_bf16(&tm_do_cls, dout, 4, dims, strides, box_cls, true);
+    if (rc) return rc;
+  }
+  const int smem = NSLOT * TILE_BYTES + 2 * PB_BYTES + LSD_FLOATS * 4 + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(space_attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  const int grid = G.groups < num_sms() ? G.groups : num_sms();
+  space_attn_bwd_tc_kernel<<<grid, THREADS, smem, st>>>(tm_rows, tm_cls, tm_do_rows, tm_do_cls,
+                                                        reinterpret_cast<const bf16*>(out), lse,
+                                                        reinterpret_cast<bf16*>(dqkv), dcls, q_scale, G);
+  EGOVLP_CHECK_LAUNCH();
+  return EGOVLP_OK;
+}
+
+}  // namespace egovlp

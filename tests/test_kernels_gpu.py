@@ -178,15 +178,19 @@ def test_cast_and_colsum(ops):
 @pytest.mark.parametrize("B,T,N,H,mode", [(2, 4, 196, 2, 1), (2, 4, 196, 2, 0), (1, 16, 196, 1, 0), (1, 16, 196, 1, 1),
                                           (2, 3, 4, 2, 0), (2, 3, 4, 2, 1), (3, 8, 50, 1, 0), (2, 1, 30, 1, 0),
                                           (2, 5, 196, 1, 0), (2, 8, 196, 1, 0), (1, 8, 196, 2, 1), (2, 16, 100, 1, 0),
-                                          (2, 4, 30, 1, 0), (2, 2, 20, 1, 1)])
+                                          (2, 4, 30, 1, 0), (2, 2, 20, 1, 1), (3, 16, 196, 8, 1), (2, 4, 150, 2, 1)])
 def test_divided_attention_fwd_bwd(ops, B, T, N, H, mode, generic, monkeypatch):
     """Both implementations (specialised span kernels; generic group-id kernels) against the oracle's restatement
     of VarAttention's core, incl. partially filled time groups (N not a multiple of the patches per group)."""
     from oracle import reference_port as rp
-    # False: default dispatch (mma.sync span kernels); "tc": tcgen05/TMEM space forward; True: generic group-id kernels
+    # False: default dispatch (mma.sync span kernels, tcgen05 space backward); "tc": + tcgen05/TMEM space forward;
+    # True: generic group-id kernels; "w8": 8-warp time backward and the mma.sync space backward (EGOVLP_ATTN_TC_BWD=0).
+    # (3, 16, 196, 8, 1) has 384 groups: the persistent tcgen05 kernels loop 2-3 times per CTA (ring / parity logic);
+    # (2, 4, 150, 2, 1) exercises a short second tile (151 keys -> 160 padded, W1 = 32).
     monkeypatch.setenv("EGOVLP_ATTN_GENERIC", "1" if generic is True else "0")
     monkeypatch.setenv("EGOVLP_ATTN_TC", "1" if generic == "tc" else "0")
     monkeypatch.setenv("EGOVLP_ATTN_TIME_BWD_WARPS", "8" if generic == "w8" else "4")   # both time-backward shapes
+    monkeypatch.setenv("EGOVLP_ATTN_TC_BWD", "0" if generic == "w8" else "1")
     S, D = 1 + T * N, 64 * H
     qkv = mk((B * S, 3 * D), 50 + T + mode, 1.0)
     scale = 0.125
