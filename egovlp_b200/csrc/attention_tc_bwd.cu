@@ -341,10 +341,11 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         {
           uint32_t sv[64];
           if (active) {
+            // always the full 64 columns in two wide loads (columns past ncol are stale TMEM, masked below): narrow
+            // tcgen05.ld shapes pay a fixed per-instruction cost that dominated the first version of this kernel
             const uint32_t a = tmem + lane_base + S_COL + col0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c)
-              if (8 * c < ncol) tmem_ld8(a + 8 * c, sv + 8 * c);
+            tmem_ld32(a, sv);
+            tmem_ld32(a + 32, sv + 32);
             tmem_ld_wait();
           }
           warp_arrive(s_free, lane);
@@ -381,10 +382,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         for (int hh = 0; hh < 2; ++hh) {
           if (active && 32 * hh < ncol) {
             uint32_t dp[32];
-            const uint32_t a = tmem + lane_base + DP_COL + col0 + 32 * hh;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (32 * hh + 8 * c < ncol) tmem_ld8(a + 8 * c, dp + 8 * c);
+            tmem_ld32(tmem + lane_base + DP_COL + col0 + 32 * hh, dp);
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {

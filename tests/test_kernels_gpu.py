@@ -116,8 +116,10 @@ def test_gemm_strided_views(ops, gemm_mode):
     assert torch.all(obuf[:, :N] == 0)
 
 
-@pytest.mark.parametrize("rows,D", [(1000, 768), (37, 64), (785 * 2, 768), (5, 128)])
+@pytest.mark.parametrize("rows,D", [(1000, 768), (37, 64), (785 * 2, 768), (5, 128), (4999, 768), (6001, 128),
+                                    (3137 * 4, 768)])
 def test_layernorm_fwd_bwd(ops, rows, D):
+    """rows >= 4096 with D % 128 == 0 take the bulk-copy pipelined kernels (ragged last tile at 4999 / 6001 rows)."""
     x = mk((rows, D), 20, 2.0, torch.float32) + 0.3
     g, b = mk((D,), 21, dtype=torch.float32) * 0.1 + 1, mk((D,), 22, dtype=torch.float32) * 0.1
     y16 = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
