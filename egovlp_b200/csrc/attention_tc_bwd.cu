@@ -55,11 +55,113 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void st_shared_v4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
+// Bounded mbarrier wait for the hot roles: try_wait suspends in hardware; the clock is only looked at every 1024
+// polls (a protocol bug traps the launch after a few seconds instead of hanging), so a waiting warp costs almost no issue slots (the generic mbar_wait spends ~8 instructions per poll, which
+// showed up as 18 M instructions each for the TMA and the MMA warp in the first profile of this kernel).
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (int outer = 0; outer < (1 << 22); ++outer) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+  }
+  __trap();        // no printf here: a call site in the wait makes every live register of the caller spill around it
+}
+#define mbar_wait mbar_wait_hot
+
 // arrive (one per warp) after this warp's TMEM reads / generic-proxy smem writes are complete
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
+}
+
+struct SoftmaxArgs {
+  float lse2, delta;
+  uint32_t s_addr, dp_addr, p_row, ds_row, sw;
+  int col0, ncol, vis_cols, lane;
+  uint32_t parity, s_full, s_free, p_freeb, p_ready, dp_full, ds_freeb;
+  bool active;
+};
+
+// One (key tile, query tile) step of a softmax thread: S (TMEM) -> P = exp2(S log2e - lse2) -> bf16 smem, then
+// dP (TMEM) -> dS = P (dP - delta) -> bf16 smem.  MASKED = the short second key tile (<= 40 columns per thread, CLS key
+// and padding keys masked per element); the first key tile is dense: 64 columns, packed FFMA2 / FMUL2 / FADD2 math and no
+// predicates (the first profile of this kernel was instruction-issue bound: 12 instructions per element in this loop).
+template <bool MASKED>
+__device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
+  constexpr int NCH = MASKED ? 5 : 8;                    // 8-column chunks handled by a thread
+  const f32x2 nl2 = pk2(-A.lse2, -A.lse2), l2e = pk2(LOG2E, LOG2E), ndel = pk2(-A.delta, -A.delta);
+  mbar_wait(A.s_full, A.parity);
+  tc_fence_after();
+  mbar_wait(A.p_freeb, A.parity ^ 1);                    // the previous step's dV has consumed the P buffer (long ago)
+  {
+    uint32_t sv[64];
+    if (A.active) {
+      // always two wide loads (columns past ncol are stale TMEM, never used): narrow tcgen05.ld shapes pay a fixed
+      // per-instruction cost that dominated the first version of this kernel
+      tmem_ld32(A.s_addr, sv);
+      tmem_ld32(A.s_addr + 32, sv + 32);
+      tmem_ld_wait();
+    }
+    warp_arrive(A.s_free, A.lane);
+    if (A.active) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (!MASKED || 8 * c < A.ncol) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float e0, e1;
+            up2(fma2(pk2(__uint_as_float(sv[8 * c + 2 * j]), __uint_as_float(sv[8 * c + 2 * j + 1])), l2e, nl2), e0, e1);
+            e0 = exp2f(e0);
+            e1 = exp2f(e1);
+            if (MASKED) {
+              e0 = 8 * c + 2 * j < A.vis_cols ? e0 : 0.f;
+              e1 = 8 * c + 2 * j + 1 < A.vis_cols ? e1 : 0.f;
+            }
+            pk[j] = pack_bf16x2(e0, e1);
+          }
+          const int col = A.col0 + 8 * c;
+          st_shared_v4(A.p_row + (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+  fence_proxy_async_smem();                              // generic-proxy stores -> visible to the UMMA reads
+  warp_arrive(A.p_ready, A.lane);
+
+  // dP -> dS = P (dP - delta), 32 columns at a time; P is read back from this thread's own smem row (bf16, exactly what
+  // dV consumes) instead of being held in 32 registers across the wait.  Masked / padded elements have P == 0 and a
+  // finite dP, so no predicate is needed here.
+  mbar_wait(A.dp_full, A.parity);
+  tc_fence_after();
+  mbar_wait(A.ds_freeb, A.parity ^ 1);                   // the previous step's dK / dQ have consumed the dS buffer
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    if (A.active && (!MASKED || 32 * hh < A.ncol)) {
+      uint32_t dp[32];
+      tmem_ld32(A.dp_addr + 32 * hh, dp);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (4 * hh + c < NCH && (!MASKED || 32 * hh + 8 * c < A.ncol)) {
+          const int col = A.col0 + 32 * hh + 8 * c;
+          const uint32_t off = (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4);
+          uint32_t pk[4], dsp[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(A.p_row + off));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d0, d1;
+            up2(mul2(pk2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)),
+                     add2(pk2(__uint_as_float(dp[8 * c + 2 * j]), __uint_as_float(dp[8 * c + 2 * j + 1])), ndel)), d0, d1);
+            dsp[j] = pack_bf16x2(d0, d1);
+          }
+          st_shared_v4(A.ds_row + off, dsp[0], dsp[1], dsp[2], dsp[3]);
+        }
+      }
+    }
+  }
 }
 
 // 32 fp32 accumulator values of one row -> 64 contiguous bytes of bf16
@@ -332,78 +434,25 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const int nvis = rvalid ? ((row == G.N && f != 0) ? G.N : G.NK) : 0;
         const int ncol = kt ? (hf ? G.W1 - half1 : half1) : 64;     // this thread's columns of the key tile
         const int col0 = kt ? hf * half1 : hf * 64;
-        const float lse2 = rvalid ? lse2_s[row] : 0.f, delta = rvalid ? delta_s[row] : 0.f;
-        uint32_t pk[32];                                 // P of this thread's columns, bf16 pairs (what dV consumes)
-
-        // ---- S -> P
-        mbar_wait(s_full, n & 1);
-        tc_fence_after();
-        {
-          uint32_t sv[64];
-          if (active) {
-            // always the full 64 columns in two wide loads (columns past ncol are stale TMEM, masked below): narrow
-            // tcgen05.ld shapes pay a fixed per-instruction cost that dominated the first version of this kernel
-            const uint32_t a = tmem + lane_base + S_COL + col0;
-            tmem_ld32(a, sv);
-            tmem_ld32(a + 32, sv + 32);
-            tmem_ld_wait();
-          }
-          warp_arrive(s_free, lane);
-          if (active) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool ok0 = 2 * j < ncol && kt * 128 + col0 + 2 * j < nvis;
-              const bool ok1 = 2 * j + 1 < ncol && kt * 128 + col0 + 2 * j + 1 < nvis;
-              const float p0 = ok0 ? exp2f(fmaf(__uint_as_float(sv[2 * j]), LOG2E, -lse2)) : 0.f;
-              const float p1 = ok1 ? exp2f(fmaf(__uint_as_float(sv[2 * j + 1]), LOG2E, -lse2)) : 0.f;
-              pk[j] = pack_bf16x2(p0, p1);
-            }
-          }
-        }
-        mbar_wait(p_freeb, (n & 1) ^ 1);                 // the previous step's dV has consumed the P buffer
-        if (active) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (8 * c < ncol) {
-              const int col = col0 + 8 * c;
-              const uint32_t a = sP + (col >> 6) * KBLK_BYTES + r_in * ROWB + ((((col & 63) >> 3) ^ (r_in & 7)) << 4);
-              st_shared_v4(a, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-            }
-          }
-        }
-        fence_proxy_async_smem();                        // generic-proxy stores -> visible to the UMMA reads
-        warp_arrive(p_ready, lane);
-
-        // ---- dP -> dS = P (dP - delta), 32 columns at a time
-        mbar_wait(dp_full, n & 1);
-        tc_fence_after();
-        mbar_wait(ds_freeb, (n & 1) ^ 1);                // the previous step's dK / dQ have consumed the dS buffer
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (active && 32 * hh < ncol) {
-            uint32_t dp[32];
-            tmem_ld32(tmem + lane_base + DP_COL + col0 + 32 * hh, dp);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if (32 * hh + 8 * c < ncol) {
-                uint32_t dsp[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const uint32_t pp = pk[16 * hh + 4 * c + j];
-                  const float p0 = __uint_as_float(pp << 16), p1 = __uint_as_float(pp & 0xffff0000u);
-                  // masked / padded elements have P == 0 exactly: their dP may be garbage (rows beyond the tile)
-                  const float d0 = p0 != 0.f ? p0 * (__uint_as_float(dp[8 * c + 2 * j]) - delta) : 0.f;
-                  const float d1 = p1 != 0.f ? p1 * (__uint_as_float(dp[8 * c + 2 * j + 1]) - delta) : 0.f;
-                  dsp[j] = pack_bf16x2(d0, d1);
-                }
-                const int col = col0 + 32 * hh + 8 * c;
-                const uint32_t sa = sDS + (col >> 6) * KBLK_BYTES + r_in * ROWB + ((((col & 63) >> 3) ^ (r_in & 7)) << 4);
-                st_shared_v4(sa, dsp[0], dsp[1], dsp[2], dsp[3]);
-              }
-            }
-          }
-        }
+        // invalid (padding) rows: lse2 = +inf makes every P of the row exp2(-inf) = 0, hence dS = 0, without a mask
+        SoftmaxArgs sa;
+        sa.lse2 = rvalid ? lse2_s[row] : INFINITY;
+        sa.delta = rvalid ? delta_s[row] : 0.f;
+        sa.s_addr = tmem + lane_base + S_COL + col0;
+        sa.dp_addr = tmem + lane_base + DP_COL + col0;
+        sa.p_row = sP + r_in * ROWB;
+        sa.ds_row = sDS + r_in * ROWB;
+        sa.sw = r_in & 7;
+        sa.col0 = col0;
+        sa.ncol = ncol;
+        sa.vis_cols = nvis - kt * 128 - col0;            // columns [0, vis_cols) of this thread are visible to its row
+        sa.active = active;
+        sa.lane = lane;
+        sa.parity = n & 1;
+        sa.s_full = s_full; sa.s_free = s_free; sa.p_freeb = p_freeb; sa.p_ready = p_ready;
+        sa.dp_full = dp_full; sa.ds_freeb = ds_freeb;
+        if (kt == 0) softmax_step<false>(sa);
+        else softmax_step<true>(sa);
         fence_proxy_async_smem();
         warp_arrive(dp_free, lane);
         if (lane == 0) mbar_arrive(ds_ready);            // (ordered after the fences + __syncwarp of warp_arrive)
@@ -414,21 +463,19 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           tc_fence_after();
           const int key = kt * 128 + r_in;
           const bool any = !(kt == 1 && qd * 32 >= G.W1);
-          uint32_t dk[32], dv[32];
+          bf16* rowp = dqkv + ((long long)b * G.S + 1 + f * G.N + key) * (3 * G.D) + h * HD + hf * 32;
+          float* clsp = dcls + ((long long)(b * G.H + h) * 3 + 1) * HD + hf * 32;
           if (any) {
-            tmem_ld32(tmem + lane_base + DK_COL + hf * 32, dk);
-            tmem_ld32(tmem + lane_base + DV_COL + hf * 32, dv);
-            tmem_ld_wait();
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {                  // dK, then dV: 32 registers at a time
+              uint32_t acc[32];
+              tmem_ld32(tmem + lane_base + (w ? DV_COL : DK_COL) + hf * 32, acc);
+              tmem_ld_wait();
+              if (key < G.N) store_row32(acc, 1.f, rowp + (1 + w) * G.D);
+              else if (key == G.N) atomic_row32(acc, clsp + w * HD);         // the CLS key: summed over the groups of (b, h)
+            }
           }
           warp_arrive(dkv_free, lane);
-          if (any && key < G.N) {
-            bf16* rowp = dqkv + ((long long)b * G.S + 1 + f * G.N + key) * (3 * G.D) + h * HD + hf * 32;
-            store_row32(dk, 1.f, rowp + G.D);
-            store_row32(dv, 1.f, rowp + 2 * G.D);
-          } else if (any && key == G.N) {                // the CLS key: summed over every group of (b, h)
-            atomic_row32(dk, dcls + ((long long)(b * G.H + h) * 3 + 1) * HD + hf * 32);
-            atomic_row32(dv, dcls + ((long long)(b * G.H + h) * 3 + 2) * HD + hf * 32);
-          }
         }
       }
 
@@ -437,21 +484,21 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       mbar_wait(dq_full, gi & 1);
       tc_fence_after();
       {
-        uint32_t dq0[32], dq1[32];
-        const bool any1 = qd * 32 < G.W1;
-        tmem_ld32(tmem + lane_base + DQ_COL + hf * 32, dq0);
-        if (any1) tmem_ld32(tmem + lane_base + DQ_COL + 64 + hf * 32, dq1);
-        tmem_ld_wait();
-        warp_arrive(dq_free, lane);
         // the CLS query (row N): raw sum over the groups of (b, h), scaled by cls_grad_finalize_kernel
         bf16* q0 = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD + hf * 32;
         float* cls_q = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD + hf * 32;
-        if (r_in < G.N) store_row32(dq0, q_scale, q0 + (long long)r_in * (3 * G.D));
-        if (any1) {
-          const int row = 128 + r_in;
-          if (row < G.N) store_row32(dq1, q_scale, q0 + (long long)row * (3 * G.D));
-          else if (row == G.N) atomic_row32(dq1, cls_q);
+#pragma unroll
+        for (int qt = 0; qt < 2; ++qt) {
+          if (qt == 0 || qd * 32 < G.W1) {
+            uint32_t acc[32];
+            tmem_ld32(tmem + lane_base + DQ_COL + 64 * qt + hf * 32, acc);
+            tmem_ld_wait();
+            const int row = qt * 128 + r_in;
+            if (row < G.N) store_row32(acc, q_scale, q0 + (long long)row * (3 * G.D));
+            else if (row == G.N) atomic_row32(acc, cls_q);
+          }
         }
+        warp_arrive(dq_free, lane);
       }
     }
   }
