@@ -30,11 +30,12 @@ def lib():
         _lib = C.CDLL(LIB_PATH)
         _lib.egovlp_last_error.restype = C.c_char_p
         _lib.egovlp_divided_attn_workspace_floats.restype = C.c_longlong
+        _lib.egovlp_egonce_fused_workspace_floats.restype = C.c_longlong
     return _lib
 
 
 # kernels launched per C-ABI call (memsets excluded) -- bench.py reports the count as `gpu_launches`
-_KERNELS_PER_CALL = {"egovlp_divided_attn_fwd": 2, "egovlp_divided_attn_bwd": 2, "egovlp_video_embed_bwd": 2,
+_KERNELS_PER_CALL = {"egovlp_egonce_fused_max_g": 0, "egovlp_divided_attn_fwd": 2, "egovlp_divided_attn_bwd": 2, "egovlp_video_embed_bwd": 2,
                      "egovlp_nce_fwd": 2, "egovlp_dual_softmax": 2}
 _launches = 0
 

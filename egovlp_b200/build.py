@@ -22,7 +22,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 # IEEE fp32 (no --use_fast_math: no approximate division / sqrt / exp, no flush-to-zero) where the reference computes in
 # fp32 and the results are compared at fp32 rounding level or bit-exactly: losses, ranking metrics, EgoMCQ, AdamW.
-IEEE_SOURCES = {"loss.cu", "retrieval.cu", "optim.cu"}
+IEEE_SOURCES = {"loss.cu", "loss_fused.cu", "retrieval.cu", "optim.cu"}
 
 
 def flags_for(src):

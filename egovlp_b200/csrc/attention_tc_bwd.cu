@@ -15,10 +15,12 @@
 //   warp 1     MMA issuer (one thread): S and dP of the next step are issued as soon as the softmax warps have pulled the
 //              current ones out of TMEM; dV after P is in smem, dK / dQ after dS
 //   warp 2     TMEM allocator: 512 columns = S 128 | dP 128 | dQ_0 64 | dQ_1 64 | dK 64 | dV 64
-//   warps 4-11 two threads per query row (64 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) -> smem,
-//              dS = P (dP - delta) -> smem, and the accumulator drains (dK / dV per key tile, dQ per group) straight to
-//              dqkv as 64-byte row pieces; CLS-row gradients by fp32 atomics.  delta = rowsum(dO o O) is computed per group
-//              from O rows prefetched during the previous group's drain.
+//   warps 4-11 softmax: two threads per query row (64 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) ->
+//              smem (packed FFMA2 + MUFU, no predicates on the dense first key tile), dS = P (dP - delta) -> smem
+//   warps 12-15 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
+//              buffered), and the accumulator drains (dK / dV per key tile, dQ per group) straight to dqkv as 64-byte row
+//              pieces, CLS-row gradients by fp32 atomics -- so the softmax warps never wait for a drain or a prologue.
+// setmaxnreg splits the register file 72 / 176 / 88 per thread between the control, softmax and drain warpgroups.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -36,19 +38,13 @@ constexpr int NSLOT = 6;
 constexpr int PB_BYTES = 2 * 128 * ROWB;              // [2 key blocks of 64][128 query rows][128 B]
 constexpr int KBLK_BYTES = 128 * ROWB;                // one 64-key block
 constexpr int LSD_FLOATS = 2 * 2 * TILE_ROWS;         // [parity][lse2 | delta][row]
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;                          // warpgroups: control (TMA / MMA / TMEM) | softmax x2 | drain
 constexpr int S_COL = 0, DP_COL = 128, DQ_COL = 256, DK_COL = 384, DV_COL = 448;
 
 struct BwdGeom {
   int B, H, T, N, S, D, NK, NKP, W1, groups;        // W1 = NKP - 128: width of the second key / query tile
 };
 
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(r));
 }
@@ -182,8 +178,8 @@ __device__ __forceinline__ void atomic_row32(const uint32_t (&v)[32], float* dst
 __global__ void __launch_bounds__(THREADS, 1)
 space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_cls,
                          const __grid_constant__ CUtensorMap tm_do_rows, const __grid_constant__ CUtensorMap tm_do_cls,
-                         const bf16* __restrict__ out, const float* __restrict__ lse_in, bf16* __restrict__ dqkv,
-                         float* __restrict__ dcls, float q_scale, BwdGeom G) {
+                         const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse_in,
+                         bf16* __restrict__ dqkv, float* __restrict__ dcls, float q_scale, BwdGeom G) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -196,7 +192,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t s_full = bars + 96, s_free = bars + 104, dp_full = bars + 112, dp_free = bars + 120;
   const uint32_t p_ready = bars + 128, p_freeb = bars + 136, ds_ready = bars + 144, ds_freeb = bars + 152;
   const uint32_t dkv_full = bars + 160, dkv_free = bars + 168, dq_full = bars + 176, dq_free = bars + 184;
-  const uint32_t tmem_slot = bars + 192;
+  const uint32_t lsd_ready = bars + 192, lsd_taken = bars + 200;
+  const uint32_t tmem_slot = bars + 208;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,8 +217,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     mbar_init(dp_full, 1);  mbar_init(dp_free, 8);
     mbar_init(p_ready, 8);  mbar_init(p_freeb, 1);
     mbar_init(ds_ready, 8); mbar_init(ds_freeb, 1);
-    mbar_init(dkv_full, 1); mbar_init(dkv_free, 8);
-    mbar_init(dq_full, 1);  mbar_init(dq_free, 8);
+    mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
+    mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
+    mbar_init(lsd_ready, 4); mbar_init(lsd_taken, 8);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -232,7 +230,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t tmem = *tmem_slot_ptr;
   const int ksteps1 = G.W1 / 16;                        // contraction steps over the second (short) tile
 
-  // register budget: the three single-thread roles give registers back, the softmax warps take them (168 -> 216, 72 for the others)
+  // register budget: the three single-thread roles give registers back, the softmax warps take them (launch: 128 each; control 72, drain 88, softmax 176)
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
@@ -357,73 +355,21 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       }
     }
   }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
-    // ============================== softmax / dS / drains ==============================
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    // ============================== softmax / dS ==============================
     const int qd = warp & 3, hf = (warp - 4) >> 2;
     const int r_in = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const int tid_c = threadIdx.x - 128;                 // 0..255: the row this thread prepares (lse, delta)
     const int half1 = ((G.W1 / 8 + 1) / 2) * 8;          // columns of half 0 in the short key tile (multiple of 8)
-
-    // O row + lse of row tid_c of group g: pulled into L2 one group ahead (no registers held across the group), read at
-    // the top of the group
-    auto row_ptrs = [&](int g, const uint4*& orow, const float*& lrow) {
-      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
-      const int tok = tid_c < G.N ? 1 + f * G.N + tid_c : 0;
-      orow = reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD);
-      lrow = lse_in + ((long long)(b * G.H + h)) * G.S + tok;
-    };
-    auto prefetch_rows = [&](int g) {
-      if (g < G.groups && tid_c < G.NK) {
-        const uint4* orow; const float* lrow;
-        row_ptrs(g, orow, lrow);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(orow));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(lrow));
-      }
-    };
-    prefetch_rows(blockIdx.x);
-
     int gi = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
-      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
-      const int c0 = 4 * gi;
-      float* lse2_s = lsd + (gi & 1) * 2 * TILE_ROWS;
-      float* delta_s = lse2_s + TILE_ROWS;
-      // ---- per-row lse (log2 units) and delta = rowsum(dO o O)
-      {
-        const uint32_t slot = (c0 + 2) % NSLOT;
-        uint4 o_pre[8];
-        float lse_pre = 0.f;
-        if (tid_c < G.NK) {
-          const uint4* orow; const float* lrow;
-          row_ptrs(g, orow, lrow);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) o_pre[i] = __ldg(orow + i);
-          lse_pre = __ldg(lrow);
-        }
-        mbar_wait(tile_full + 8 * slot, ((c0 + 2) / NSLOT) & 1);
-        if (tid_c < G.NK) {
-          const uint8_t* dorow = gen + slot * TILE_BYTES + tid_c * ROWB;
-          float d = 0.f;
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint4 dv = *reinterpret_cast<const uint4*>(dorow + ((cc ^ (tid_c & 7)) << 4));
-            const uint4 ov = o_pre[cc];
-            const uint32_t du[4] = {dv.x, dv.y, dv.z, dv.w}, ou[4] = {ov.x, ov.y, ov.z, ov.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 a = unpack_bf16x2(ou[i]), bb = unpack_bf16x2(du[i]);
-              d = fmaf(a.x, bb.x, d);
-              d = fmaf(a.y, bb.y, d);
-            }
-          }
-          lse2_s[tid_c] = lse_pre * LOG2E;
-          delta_s[tid_c] = d;
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-
+      const int f = g % G.T;
+      const float* lse2_s = lsd + (gi & 1) * 2 * TILE_ROWS;
+      const float* delta_s = lse2_s + TILE_ROWS;
+      mbar_wait(lsd_ready, gi & 1);                      // the drain warpgroup has prepared this group's lse2 / delta
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lsd_taken);             // ... and may now prepare the next one (one phase ahead at most)
 #pragma unroll 1
       for (int it = 0; it < 4; ++it) {
         const int n = 4 * gi + it, kt = it >> 1, qt = it & 1;
@@ -456,50 +402,93 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         fence_proxy_async_smem();
         warp_arrive(dp_free, lane);
         if (lane == 0) mbar_arrive(ds_ready);            // (ordered after the fences + __syncwarp of warp_arrive)
-
-        // ---- key tile complete: drain dK / dV rows (keys kt*128 + r_in), this thread's 32 of the 64 columns
-        if (qt == 1) {
-          mbar_wait(dkv_full, (2 * gi + kt) & 1);
-          tc_fence_after();
-          const int key = kt * 128 + r_in;
-          const bool any = !(kt == 1 && qd * 32 >= G.W1);
-          bf16* rowp = dqkv + ((long long)b * G.S + 1 + f * G.N + key) * (3 * G.D) + h * HD + hf * 32;
-          float* clsp = dcls + ((long long)(b * G.H + h) * 3 + 1) * HD + hf * 32;
-          if (any) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {                  // dK, then dV: 32 registers at a time
-              uint32_t acc[32];
-              tmem_ld32(tmem + lane_base + (w ? DV_COL : DK_COL) + hf * 32, acc);
-              tmem_ld_wait();
-              if (key < G.N) store_row32(acc, 1.f, rowp + (1 + w) * G.D);
-              else if (key == G.N) atomic_row32(acc, clsp + w * HD);         // the CLS key: summed over the groups of (b, h)
-            }
-          }
-          warp_arrive(dkv_free, lane);
-        }
       }
+    }
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    // ============================== drain warpgroup ==============================
+    // (1) per-row lse (log2 units) and delta = rowsum(dO o O) of the NEXT group, straight from global memory (so it
+    //     does not wait for the TMA ring), double-buffered by group parity; (2) the accumulator drains: dK / dV after
+    //     each key tile, dQ at the end of the group -- 64-byte row pieces to dqkv, CLS rows by fp32 atomics.  The softmax
+    //     warps never wait for either.
+    const int qd = warp & 3;
+    const int r_in = qd * 32 + lane;                     // TMEM lane = accumulator row owned by this thread
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const int t128 = threadIdx.x - 384;                  // 0..127
 
-      // ---- next group's O rows / lse on their way while the dQ accumulators are drained
-      prefetch_rows(g + gridDim.x);
+    auto prepare_rows = [&](int g, int par) {
+      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+      float* lse2_s = lsd + par * 2 * TILE_ROWS;
+      float* delta_s = lse2_s + TILE_ROWS;
+#pragma unroll 1
+      for (int row = t128; row < G.NK; row += 128) {
+        const long long tok = (long long)b * G.S + (row < G.N ? 1 + f * G.N + row : 0);
+        const uint4* orow = reinterpret_cast<const uint4*>(out + tok * G.D + h * HD);
+        const uint4* drow = reinterpret_cast<const uint4*>(dout + tok * G.D + h * HD);
+        uint4 ov[8], dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ov[i] = __ldg(orow + i); dv[i] = __ldg(drow + i); }
+        const float l = __ldg(lse_in + ((long long)(b * G.H + h)) * G.S + (row < G.N ? 1 + f * G.N + row : 0));
+        float d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t ou[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w}, du[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 a = unpack_bf16x2(ou[k]), bb = unpack_bf16x2(du[k]);
+            d = fmaf(a.x, bb.x, d);
+            d = fmaf(a.y, bb.y, d);
+          }
+        }
+        lse2_s[row] = l * LOG2E;
+        delta_s[row] = d;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lsd_ready);             // mbarrier arrive = release: the smem writes above are visible
+    };
+    auto drain_row = [&](uint32_t col, float scale, bf16* dst_row, float* dst_cls, bool is_row, bool is_cls) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t acc[32];
+        tmem_ld32(tmem + lane_base + col + hf * 32, acc);
+        tmem_ld_wait();
+        if (is_row) store_row32(acc, scale, dst_row + hf * 32);
+        else if (is_cls) atomic_row32(acc, dst_cls + hf * 32);
+      }
+    };
+
+    if ((int)blockIdx.x < G.groups) prepare_rows(blockIdx.x, 0);
+    int gi = 0;
+    for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
+      const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
+      // the next group's lse2 / delta: its buffer (parity gi + 1) was last read in group gi - 1, whose dQ this warpgroup
+      // has already drained, i.e. every softmax warp is past it
+      if (g + (int)gridDim.x < G.groups) {
+        mbar_wait(lsd_taken, gi & 1);                    // every softmax warp has seen phase gi of lsd_ready
+        prepare_rows(g + gridDim.x, (gi + 1) & 1);
+      }
+      bf16* base_row = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD;
+      float* cls = dcls + ((long long)(b * G.H + h) * 3) * HD;
+#pragma unroll 1
+      for (int kt = 0; kt < 2; ++kt) {
+        mbar_wait(dkv_full, (2 * gi + kt) & 1);
+        tc_fence_after();
+        const int key = kt * 128 + r_in;
+        if (!(kt == 1 && qd * 32 >= G.W1)) {
+          drain_row(DK_COL, 1.f, base_row + (long long)key * (3 * G.D) + G.D, cls + HD, key < G.N, key == G.N);
+          drain_row(DV_COL, 1.f, base_row + (long long)key * (3 * G.D) + 2 * G.D, cls + 2 * HD, key < G.N, key == G.N);
+        }
+        warp_arrive(dkv_free, lane);
+      }
       mbar_wait(dq_full, gi & 1);
       tc_fence_after();
-      {
-        // the CLS query (row N): raw sum over the groups of (b, h), scaled by cls_grad_finalize_kernel
-        bf16* q0 = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD + hf * 32;
-        float* cls_q = dcls + ((long long)(b * G.H + h) * 3 + 0) * HD + hf * 32;
-#pragma unroll
-        for (int qt = 0; qt < 2; ++qt) {
-          if (qt == 0 || qd * 32 < G.W1) {
-            uint32_t acc[32];
-            tmem_ld32(tmem + lane_base + DQ_COL + 64 * qt + hf * 32, acc);
-            tmem_ld_wait();
-            const int row = qt * 128 + r_in;
-            if (row < G.N) store_row32(acc, q_scale, q0 + (long long)row * (3 * G.D));
-            else if (row == G.N) atomic_row32(acc, cls_q);
-          }
-        }
-        warp_arrive(dq_free, lane);
+#pragma unroll 1
+      for (int qt = 0; qt < 2; ++qt) {
+        const int row = qt * 128 + r_in;                 // the CLS query (row N): raw sum, scaled by cls_grad_finalize_kernel
+        if (qt == 0 || qd * 32 < G.W1)
+          drain_row(DQ_COL + 64 * qt, q_scale, base_row + (long long)row * (3 * G.D), cls, row < G.N, row == G.N);
       }
+      warp_arrive(dq_free, lane);
     }
   }
 
@@ -555,7 +544,8 @@ int space_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const 
   }
   const int grid = G.groups < num_sms() ? G.groups : num_sms();
   space_attn_bwd_tc_kernel<<<grid, THREADS, smem, st>>>(tm_rows, tm_cls, tm_do_rows, tm_do_cls,
-                                                        reinterpret_cast<const bf16*>(out), lse,
+                                                        reinterpret_cast<const bf16*>(out),
+                                                        reinterpret_cast<const bf16*>(dout), lse,
                                                         reinterpret_cast<bf16*>(dqkv), dcls, q_scale, G);
   EGOVLP_CHECK_LAUNCH();
   return EGOVLP_OK;

@@ -68,8 +68,14 @@ class PackedGather(torch.autograd.Function):
 
 
 def egoclip_step_loss(model, loss_fn, data):
-    """Forward of one EgoClip pretraining step, B200-first: model -> ONE packed gather -> fused similarity + EgoNCE
-    (positives from bit-packed tags).  Equivalent to trainer/trainer_egoclip.py:125-135."""
+    """Forward of one EgoClip pretraining step, B200-first: model -> ONE packed gather -> ONE fused similarity + EgoNCE
+    kernel reading the gathered buffer in place (positives from bit-packed tags), whose backward kernel emits the local
+    gradient slice.  Equivalent to trainer/trainer_egoclip.py:125-135."""
     text_embeds, video_embeds = model(data)
+    world, rank = _world()
+    loss = loss_fn.gathered(text_embeds, video_embeds, data["verb_vec"], data["noun_vec"], _all_gather_rows, rank, world)
+    if loss is not None:
+        return loss
+    # G > 512 (more than 8 ranks x 64 clips): packed gather + the kernel-per-stage loss path
     t, v, verb, noun = PackedGather.apply(text_embeds, video_embeds, data["verb_vec"], data["noun_vec"])
     return loss_fn.fused(t, v, verb, noun)

@@ -669,6 +669,60 @@ class NceLossFn(torch.autograd.Function):
         return ops.nce_bwd(x, mask, stats, ctx.inv_temp, g.contiguous().float()), None, None
 
 
+class FusedEgoNceFn(torch.autograd.Function):
+    """sim_matrix + EgoNCE / InfoNCE from the gathered embeddings and multi-hot tags in ONE kernel per direction
+    (csrc/loss_fused.cu; reference trainer/trainer_egoclip.py:130-135).  `text` / `video` [G, C], `verb` / `noun`
+    [G, n] are fp32 row-strided views (e.g. column slices of the packed all-gather buffer, read in place).  Gradients
+    are produced for rows [row0, row0 + n_local) only and returned zero-padded to [G, C] when n_local < G is not the
+    whole matrix -- `GatherEgoNceFn` below hands the local slice out directly instead."""
+
+    @staticmethod
+    def forward(ctx, text, video, verb, noun, temperature, mode):
+        loss, saved = ops.egonce_fused_fwd(text, video, verb, noun, 1.0 / temperature, mode)
+        ctx.args = (1.0 / temperature, mode, verb.shape[1] if verb is not None else 0,
+                    noun.shape[1] if noun is not None else 0)
+        ctx.save_for_backward(text, video, *saved)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        text, video, *saved = ctx.saved_tensors
+        inv_temp, mode, nv, nn_ = ctx.args
+        dt, dv = ops.egonce_fused_bwd(text, video, saved, nv, nn_, inv_temp, mode, g.contiguous().float(), 0,
+                                      text.shape[0])
+        return dt, dv, None, None, None, None
+
+
+class GatherEgoNceFn(torch.autograd.Function):
+    """The exchange step of the data-parallel training step, fused with the loss: local embeddings + tags -> ONE packed
+    all-gather (one pack launch, one ncclAllGather) -> the fused EgoNCE kernel on column views of the gathered buffer ->
+    loss; the backward kernel emits d text / d video of THIS rank's rows only (the reference's AllGather_multi backward,
+    trainer/trainer_egoclip.py:23-27).  `gather(packed_local) -> packed_all` is the collective (identity at world 1)."""
+
+    @staticmethod
+    def forward(ctx, text, video, verb, noun, temperature, mode, gather, rank):
+        B, Ct = text.shape
+        Cv, nv, nn_ = video.shape[1], verb.shape[1], noun.shape[1]
+        assert Ct == Cv
+        packed = ops.pack_rows4(text.contiguous().float(), video.contiguous().float(), verb.contiguous().float(),
+                                noun.contiguous().float())
+        allp = gather(packed)                              # [world * B, Ct + Cv + nv + nn], rank-major
+        t, v = allp[:, :Ct], allp[:, Ct:Ct + Cv]
+        vb, nb_ = allp[:, Ct + Cv:Ct + Cv + nv], allp[:, Ct + Cv + nv:]
+        loss, saved = ops.egonce_fused_fwd(t, v, vb, nb_, 1.0 / temperature, mode)
+        ctx.args = (1.0 / temperature, mode, nv, nn_, Ct, Cv, rank * B, B)
+        ctx.save_for_backward(allp, *saved)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        allp, *saved = ctx.saved_tensors
+        inv_temp, mode, nv, nn_, Ct, Cv, row0, B = ctx.args
+        dt, dv = ops.egonce_fused_bwd(allp[:, :Ct], allp[:, Ct:Ct + Cv], saved, nv, nn_, inv_temp, mode,
+                                      g.contiguous().float(), row0, B)
+        return dt, dv, None, None, None, None, None, None
+
+
 class MaxMarginFn(torch.autograd.Function):
     """MaxMarginRankingLoss (model/loss.py:63-90) and, with `row_weight`, AdaptiveMaxMarginRankingLoss
     (model/loss.py:100-133); no host-side index building.  The weight gets no gradient (the reference feeds the

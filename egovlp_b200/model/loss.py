@@ -38,9 +38,23 @@ class EgoNCE(nn.Module):
     def fused(self, text_embeds, video_embeds, verb_vec, noun_vec):
         """B200-first entry: gathered embeddings + multi-hot tags -> loss, without materialising the
         verb/noun similarity matrices (positives from bit-packed tag co-occurrence)."""
-        mask = ops.positives_mask_from_tags(verb_vec, noun_vec, self._mode())
+        G, Cc = text_embeds.shape
+        if ops.egonce_fused_supported(G, Cc) and video_embeds.shape[1] == Cc:      # ONE kernel per direction
+            f = lambda t: t if (t.dtype == torch.float32 and t.stride(1) == 1) else t.float().contiguous()
+            mode = self._mode()
+            return engine.FusedEgoNceFn.apply(f(text_embeds), f(video_embeds), f(verb_vec) if mode in (1, 3) else None,
+                                              f(noun_vec) if mode in (1, 2) else None, self.temperature, mode)
+        mask = ops.positives_mask_from_tags(verb_vec, noun_vec, self._mode())           # G > 512: kernel-per-stage path
         x = engine.SimMatrixFn.apply(text_embeds, video_embeds, 1e-8)
         return engine.NceLossFn.apply(x, mask, self.temperature)
+
+    def gathered(self, text_local, video_local, verb_local, noun_local, gather, rank, world):
+        """Data-parallel entry: local rows in, loss out; the packed all-gather happens inside (engine.GatherEgoNceFn)."""
+        G, Cc = text_local.shape[0] * world, text_local.shape[1]
+        if ops.egonce_fused_supported(G, Cc) and video_local.shape[1] == Cc:
+            return engine.GatherEgoNceFn.apply(text_local, video_local, verb_local, noun_local, self.temperature,
+                                               self._mode(), gather, rank)
+        return None
 
 
 class MaxMarginRankingLoss(nn.Module):

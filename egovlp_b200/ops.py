@@ -359,6 +359,68 @@ def nce_bwd(x, mask, stats, inv_temp, gscale):
     return dx
 
 
+def pack_rows4(a, b, c, d):
+    """[a | b | c | d] along dim 1 (fp32, row-major) in one launch: the send buffer of the packed all-gather."""
+    for t in (a, b, c, d):
+        _chk(t, F32, "pack_rows4 input"); assert t.dim() == 2 and t.is_contiguous() and t.shape[0] == a.shape[0]
+    out = torch.empty(a.shape[0], a.shape[1] + b.shape[1] + c.shape[1] + d.shape[1], dtype=F32, device=a.device)
+    call("egovlp_pack_rows4", _ptr(a), a.shape[1], _ptr(b), b.shape[1], _ptr(c), c.shape[1], _ptr(d), d.shape[1], _ptr(out),
+         a.shape[0], _stream())
+    return out
+
+
+_fused_ws = {}
+
+
+def egonce_fused_supported(G, C):
+    return G <= lib().egovlp_egonce_fused_max_g() and C <= 256
+
+
+def _rows_view(t, name):
+    _chk(t, F32, name)
+    assert t.dim() == 2 and t.stride(1) == 1, f"{name}: rows with unit inner stride expected"
+    return t
+
+
+def egonce_fused_fwd(text, video, verb, noun, inv_temp, mode, eps=1e-8):
+    """ONE kernel: normalise rows -> cosine similarities (smem only) -> positives from tag bits -> masked LSEs -> loss.
+    text / video [G, C], verb [G, nv] / noun [G, nn] (or None per `mode`): row-strided fp32 views, read in place.
+    -> (loss, saved = (norm_text, norm_video, tag_bits, stats))."""
+    text, video = _rows_view(text, "text"), _rows_view(video, "video")
+    G, Cc = text.shape
+    assert video.shape == (G, Cc)
+    nv = verb.shape[1] if verb is not None else 0
+    nn_ = noun.shape[1] if noun is not None else 0
+    if verb is not None: _rows_view(verb, "verb")
+    if noun is not None: _rows_view(noun, "noun")
+    dev = text.device
+    na, nb = torch.empty(G, dtype=F32, device=dev), torch.empty(G, dtype=F32, device=dev)
+    bits = torch.empty(G, max(1, (nv + 31) // 32 + (nn_ + 31) // 32), dtype=torch.int32, device=dev)
+    stats = torch.empty(4 * G, dtype=F32, device=dev)
+    loss = torch.empty((), dtype=F32, device=dev)
+    key = (dev.index, G)
+    ws = _fused_ws.get(key)
+    if ws is None:                      # zero once: the kernel leaves its ticket word zero after every launch
+        ws = _fused_ws[key] = torch.zeros(lib().egovlp_egonce_fused_workspace_floats(G), dtype=F32, device=dev)
+    call("egovlp_egonce_fused_fwd", _ptr(text), C.c_longlong(text.stride(0)), _ptr(video), C.c_longlong(video.stride(0)),
+         _ptr(verb), C.c_longlong(verb.stride(0) if verb is not None else 0), nv, _ptr(noun),
+         C.c_longlong(noun.stride(0) if noun is not None else 0), nn_, G, Cc, C.c_float(inv_temp), int(mode), C.c_float(eps),
+         _ptr(na), _ptr(nb), _ptr(bits), _ptr(stats), _ptr(ws), _ptr(loss), _stream())
+    return loss, (na, nb, bits, stats)
+
+
+def egonce_fused_bwd(text, video, saved, n_verb, n_noun, inv_temp, mode, gscale, row0, n_local, eps=1e-8):
+    """-> (d_text, d_video) [n_local, C] of rows [row0, row0 + n_local) only."""
+    na, nb, bits, stats = saved
+    G, Cc = text.shape
+    d_text = torch.empty(n_local, Cc, dtype=F32, device=text.device)
+    d_video = torch.empty(n_local, Cc, dtype=F32, device=text.device)
+    call("egovlp_egonce_fused_bwd", _ptr(text), C.c_longlong(text.stride(0)), _ptr(video), C.c_longlong(video.stride(0)),
+         _ptr(na), _ptr(nb), _ptr(bits), n_verb, n_noun, _ptr(stats), G, Cc, C.c_float(inv_temp), int(mode), C.c_float(eps),
+         _ptr(gscale), row0, n_local, _ptr(d_text), _ptr(d_video), _stream())
+    return d_text, d_video
+
+
 def maxmargin_fwd(x, margin, fix_norm, row_weight=None):
     _chk(x, F32, "x")
     if row_weight is not None:

@@ -188,6 +188,30 @@ int egovlp_maxmargin_fwd(const float* x, const float* row_weight, int G, float m
 int egovlp_maxmargin_bwd(const float* x, const float* row_weight, int G, float margin, int fix_norm,
                          const float* gscale, float* dx, void* stream);
 int egovlp_dual_softmax(const float* sim, float* out, int rows, int cols, float temp, void* stream);
+
+/* EgoNCE from the gathered embeddings, ONE kernel per direction (trainer/trainer_egoclip.py:130-135 = sim_matrix x3 +
+ * EgoNCE.forward, model/model.py:189-197 + model/loss.py:34-53).  text / video fp32 [G, C] and the multi-hot verb / noun
+ * tags fp32 [G, n_verb] / [G, n_noun] are row-strided views (ld_*, in floats) -- e.g. column slices of ONE packed
+ * all-gather buffer, read in place.  mode: 0 InfoNCE (diagonal positives), 1 verb AND noun, 2 noun only, 3 verb only.
+ * G <= egovlp_egonce_fused_max_g(), C <= 256.  Forward outputs: norm_text / norm_video [G], tag_bits
+ * [G, ceil(n_verb/32) + ceil(n_noun/32)] (only the tag sets `mode` uses are counted), stats [4 G] (row / column
+ * log-sum-exps), loss [1]; `workspace`: egovlp_egonce_fused_workspace_floats(G) floats, ZERO before the first launch (the
+ * kernel leaves its ticket word zero again).  Backward: d text / d video [n_local, C] of rows [row0, row0 + n_local) only
+ * (the gather's backward keeps the local slice, trainer_egoclip.py:23-27); gscale = optional device scalar dL/dloss. */
+/* out[rows, ca+cb+cc+cd] = [a | b | c | d] row by row: the send buffer of the ONE packed embedding / tag all-gather that
+ * replaces the four AllGather_multi calls of trainer/trainer_egoclip.py:126-129. */
+int egovlp_pack_rows4(const float* a, int ca, const float* b, int cb, const float* c, int cc, const float* d, int cd,
+                      float* out, int rows, void* stream);
+int egovlp_egonce_fused_max_g(void);
+long long egovlp_egonce_fused_workspace_floats(int G);
+int egovlp_egonce_fused_fwd(const float* text, long long ld_t, const float* video, long long ld_v, const float* verb,
+                            long long ld_verb, int n_verb, const float* noun, long long ld_noun, int n_noun, int G, int C,
+                            float inv_temp, int mode, float eps, float* norm_text, float* norm_video, uint32_t* tag_bits,
+                            float* stats, float* workspace, float* loss, void* stream);
+int egovlp_egonce_fused_bwd(const float* text, long long ld_t, const float* video, long long ld_v, const float* norm_text,
+                            const float* norm_video, const uint32_t* tag_bits, int n_verb, int n_noun, const float* stats,
+                            int G, int C, float inv_temp, int mode, float eps, const float* gscale, int row0, int n_local,
+                            float* d_text, float* d_video, void* stream);
 int egovlp_egomcq_score(const float* text, const float* video, float* scores, long long* pred, int Q, int K, int C,
                         float eps, void* stream);
 

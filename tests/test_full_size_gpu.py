@@ -73,6 +73,47 @@ def test_full_size_loss_g512_vs_oracle():
                                rp.adaptive_max_margin_ranking_loss(xr, w), rtol=2e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("G,C,B,rank", [(512, 256, 64, 3), (96, 256, 32, 2), (9, 16, 3, 1), (40, 32, 40, 0)])
+def test_fused_gather_egonce_kernel_local_slice_and_modes(G, C, B, rank):
+    """ONE forward kernel on column views of the packed gather buffer + ONE backward kernel emitting this rank's rows,
+    against the oracle's gathered_step_loss (all G rows) -- every positives mode, ragged G / C, the zero-noun clamp."""
+    from egovlp_b200 import engine, synthetic as syn
+    from egovlp_b200.model.loss import EgoNCE
+    from oracle import reference_port as rp
+    g = torch.Generator().manual_seed(G + C)
+    t, v = torch.randn(G, C, generator=g), torch.randn(G, C, generator=g)
+    verb, noun = syn.synthetic_tags(G, seed=G)
+    world = G // B
+    sl = slice(rank * B, (rank + 1) * B)
+    # the collective is replaced by a function that drops this rank's packed rows into the pre-gathered buffer
+    allp = torch.cat([t, v, verb, noun], dim=1).cuda()
+
+    def fake_gather(packed_local):
+        torch.testing.assert_close(packed_local, allp[sl])
+        return allp
+
+    tl, vl = t[sl].cuda().requires_grad_(True), v[sl].cuda().requires_grad_(True)
+    loss = EgoNCE().gathered(tl, vl, verb[sl].cuda(), noun[sl].cuda(), fake_gather, rank, world)
+    loss.backward()
+    tr, vr = t.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    want = rp.egonce_loss(rp.sim_matrix(tr, vr), rp.sim_matrix(verb, verb), rp.sim_matrix(noun, noun))
+    want.backward()
+    torch.testing.assert_close(loss.cpu(), want.detach(), rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(tl.grad.cpu(), tr.grad[sl], rtol=3e-4, atol=2e-7)
+    torch.testing.assert_close(vl.grad.cpu(), vr.grad[sl], rtol=3e-4, atol=2e-7)
+    for kw, ref_kw in (({"noun": True, "verb": False}, {"noun": True, "verb": False}),
+                       ({"noun": False, "verb": True}, {"noun": False, "verb": True})):
+        got = EgoNCE(**kw).fused(t.cuda(), v.cuda(), verb.cuda(), noun.cuda())
+        ref = rp.egonce_loss(rp.sim_matrix(t, v), rp.sim_matrix(verb, verb), rp.sim_matrix(noun, noun), **ref_kw)
+        torch.testing.assert_close(got.cpu(), ref, rtol=2e-5, atol=2e-5)
+    # InfoNCE = diagonal positives only (mode 0) through the same kernels
+    loss0, _ = __import__("egovlp_b200.ops", fromlist=["x"]).egonce_fused_fwd(t.cuda(), v.cuda(), None, None, 20.0, 0)
+    torch.testing.assert_close(loss0.cpu(), rp.norm_softmax_loss(rp.sim_matrix(t, v)), rtol=2e-5, atol=2e-5)
+    # a second launch reuses the workspace (the ticket word is left at zero)
+    again = EgoNCE().fused(t.cuda(), v.cuda(), verb.cuda(), noun.cuda())
+    torch.testing.assert_close(again.cpu(), want.detach(), rtol=2e-5, atol=2e-5)
+
+
 def test_dual_softmax_4096_properties():
     from egovlp_b200 import ops
     g = torch.Generator().manual_seed(23)
