@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
 }
 #define mbar_wait mbar_wait_hot
 
+// Optional timeline (EGOVLP_ATTN_BWD_TRACE=<file>): CTA 0 stamps (event, group, step, clock) of its first groups into a
+// device buffer that the host dumps after the launch -- the tool the pipeline of this kernel was tuned with.
+__device__ __forceinline__ void trace_ev(unsigned long long* tr, int lane, int ev, int gi, int it) {
+  if (tr != nullptr && blockIdx.x == 0 && lane == 0 && gi < 6) {
+    const unsigned long long slot = atomicAdd(tr, 1ull);
+    if (slot < 4000) tr[1 + slot] = ((unsigned long long)(ev & 0xff) << 56) | ((unsigned long long)(gi & 0xff) << 48) |
+                                    ((unsigned long long)(it & 0xf) << 44) | (clock64() & 0xfffffffffffull);
+  }
+}
+
 // arrive (one per warp) after this warp's TMEM reads / generic-proxy smem writes are complete
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   tc_fence_before();
@@ -78,6 +88,8 @@ struct SoftmaxArgs {
   int col0, ncol, vis_cols, lane;
   uint32_t parity, s_full, s_free, p_freeb, p_ready, dp_full, ds_freeb;
   bool active;
+  unsigned long long* trace;
+  int gi, it, tl;                                        // trace: group, step, lane id to stamp with (0 on one warp only)
 };
 
 // One (key tile, query tile) step of a softmax thread: S (TMEM) -> P = exp2(S log2e - lse2) -> bf16 smem, then
@@ -90,6 +102,7 @@ __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
   const f32x2 nl2 = pk2(-A.lse2, -A.lse2), l2e = pk2(LOG2E, LOG2E), ndel = pk2(-A.delta, -A.delta);
   mbar_wait(A.s_full, A.parity);
   tc_fence_after();
+  trace_ev(A.trace, A.tl, 20, A.gi, A.it);               // softmax: s_full seen
   mbar_wait(A.p_freeb, A.parity ^ 1);                    // the previous step's dV has consumed the P buffer (long ago)
   {
     uint32_t sv[64];
@@ -101,6 +114,7 @@ __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
       tmem_ld_wait();
     }
     warp_arrive(A.s_free, A.lane);
+    trace_ev(A.trace, A.tl, 21, A.gi, A.it);             // softmax: S in registers
     if (A.active) {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -126,13 +140,14 @@ __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
   }
   fence_proxy_async_smem();                              // generic-proxy stores -> visible to the UMMA reads
   warp_arrive(A.p_ready, A.lane);
-
+  trace_ev(A.trace, A.tl, 22, A.gi, A.it);               // softmax: P written
   // dP -> dS = P (dP - delta), 32 columns at a time; P is read back from this thread's own smem row (bf16, exactly what
   // dV consumes) instead of being held in 32 registers across the wait.  Masked / padded elements have P == 0 and a
   // finite dP, so no predicate is needed here.
   mbar_wait(A.dp_full, A.parity);
   tc_fence_after();
   mbar_wait(A.ds_freeb, A.parity ^ 1);                   // the previous step's dK / dQ have consumed the dS buffer
+  trace_ev(A.trace, A.tl, 23, A.gi, A.it);               // softmax: dp_full + ds_free seen
 #pragma unroll
   for (int hh = 0; hh < 2; ++hh) {
     if (A.active && (!MASKED || 32 * hh < A.ncol)) {
@@ -179,7 +194,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __grid_constant__ CUtensorMap tm_cls,
                          const __grid_constant__ CUtensorMap tm_do_rows, const __grid_constant__ CUtensorMap tm_do_cls,
                          const bf16* __restrict__ out, const bf16* __restrict__ dout, const float* __restrict__ lse_in,
-                         bf16* __restrict__ dqkv, float* __restrict__ dcls, float q_scale, BwdGeom G) {
+                         bf16* __restrict__ dqkv, float* __restrict__ dcls, float q_scale, BwdGeom G,
+                         unsigned long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
@@ -243,6 +259,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         for (int j = 0; j < 4; ++j) {                    // Q, K, dO, V
           const int c = 4 * gi + j, slot = c % NSLOT, u = c / NSLOT;
           mbar_wait(tile_empty + 8 * slot, (u & 1) ^ 1);
+          trace_ev(trace, 0, 1, gi, j);                    // TMA: tile j issued
           const uint32_t fb = tile_full + 8 * slot, dst = base + slot * TILE_BYTES;
           mbar_expect_tx(fb, (uint32_t)G.NK * ROWB);
           if (j == 2) {
@@ -298,11 +315,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         mbar_wait(tile_full + 8 * ((c0 + 1) % NSLOT), ((c0 + 1) / NSLOT) & 1);
         mbar_wait(s_free, (n & 1) ^ 1);
         tc_fence_after();
+        trace_ev(trace, lane, 10, gi, 0);                 // MMA: S(0) issue
         issue_s(0);
         mbar_wait(tile_full + 8 * ((c0 + 2) % NSLOT), ((c0 + 2) / NSLOT) & 1);
         mbar_wait(tile_full + 8 * ((c0 + 3) % NSLOT), ((c0 + 3) / NSLOT) & 1);
         mbar_wait(dp_free, (n & 1) ^ 1);
         tc_fence_after();
+        trace_ev(trace, lane, 11, gi, 0);                 // MMA: dP(0) issue
         issue_dp(0);
       }
 #pragma unroll 1
@@ -312,8 +331,10 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const int ks_k = kt ? ksteps1 : 8;               // contraction over this key tile's rows
         // ---- dV[kt] (+)= P^T dO
         mbar_wait(p_ready, n & 1);
+        trace_ev(trace, lane, 12, gi, it);                // MMA: p_ready seen
         if (qt == 0) mbar_wait(dkv_free, ((2 * gi + kt) & 1) ^ 1);       // previous key tile's dK / dV drained
         tc_fence_after();
+        trace_ev(trace, lane, 13, gi, it);                // MMA: dV issue
         if (lane == 0) {
           for (int j = 0; j < ks_q; ++j)
             umma_bf16_ss(tmem + DV_COL, make_smem_desc_sw128(sP + j * 2048, KBLK_BYTES, 1024),
@@ -325,12 +346,15 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         if (it < 3) {
           mbar_wait(s_free, ((n + 1) & 1) ^ 1);
           tc_fence_after();
+          trace_ev(trace, lane, 10, gi, it + 1);
           issue_s(it + 1);
         }
         // ---- dK[kt] (+)= dS^T Q,  dQ[qt] (+)= dS K
         mbar_wait(ds_ready, n & 1);
+        trace_ev(trace, lane, 14, gi, it);                // MMA: ds_ready seen
         if (it == 0) mbar_wait(dq_free, (gi & 1) ^ 1);                   // previous group's dQ drained
         tc_fence_after();
+        trace_ev(trace, lane, 15, gi, it);                // MMA: dK / dQ issue
         if (lane == 0) {
           for (int j = 0; j < ks_q; ++j)
             umma_bf16_ss(tmem + DK_COL, make_smem_desc_sw128(sDS + j * 2048, KBLK_BYTES, 1024),
@@ -350,6 +374,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         if (it < 3) {
           mbar_wait(dp_free, ((n + 1) & 1) ^ 1);
           tc_fence_after();
+          trace_ev(trace, lane, 11, gi, it + 1);
           issue_dp(it + 1);
         }
       }
@@ -397,11 +422,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         sa.parity = n & 1;
         sa.s_full = s_full; sa.s_free = s_free; sa.p_freeb = p_freeb; sa.p_ready = p_ready;
         sa.dp_full = dp_full; sa.ds_freeb = ds_freeb;
+        sa.trace = trace; sa.gi = gi; sa.it = it; sa.tl = warp == 4 ? lane : 1;
         if (kt == 0) softmax_step<false>(sa);
         else softmax_step<true>(sa);
         fence_proxy_async_smem();
         warp_arrive(dp_free, lane);
         if (lane == 0) mbar_arrive(ds_ready);            // (ordered after the fences + __syncwarp of warp_arrive)
+        trace_ev(trace, sa.tl, 24, gi, it);               // softmax: dS written
       }
     }
   } else {
@@ -465,7 +492,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       // has already drained, i.e. every softmax warp is past it
       if (g + (int)gridDim.x < G.groups) {
         mbar_wait(lsd_taken, gi & 1);                    // every softmax warp has seen phase gi of lsd_ready
+        trace_ev(trace, warp == 12 ? lane : 1, 30, gi, 0);
         prepare_rows(g + gridDim.x, (gi + 1) & 1);
+        trace_ev(trace, warp == 12 ? lane : 1, 31, gi, 0);  // drain WG: next group's lse / delta ready
       }
       bf16* base_row = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD;
       float* cls = dcls + ((long long)(b * G.H + h) * 3) * HD;
@@ -473,15 +502,18 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       for (int kt = 0; kt < 2; ++kt) {
         mbar_wait(dkv_full, (2 * gi + kt) & 1);
         tc_fence_after();
+        trace_ev(trace, warp == 12 ? lane : 1, 32, gi, kt);  // drain WG: dkv_full seen
         const int key = kt * 128 + r_in;
         if (!(kt == 1 && qd * 32 >= G.W1)) {
           drain_row(DK_COL, 1.f, base_row + (long long)key * (3 * G.D) + G.D, cls + HD, key < G.N, key == G.N);
           drain_row(DV_COL, 1.f, base_row + (long long)key * (3 * G.D) + 2 * G.D, cls + 2 * HD, key < G.N, key == G.N);
         }
         warp_arrive(dkv_free, lane);
+        trace_ev(trace, warp == 12 ? lane : 1, 33, gi, kt);  // drain WG: dK / dV stored
       }
       mbar_wait(dq_full, gi & 1);
       tc_fence_after();
+      trace_ev(trace, warp == 12 ? lane : 1, 34, gi, 0);    // drain WG: dq_full seen
 #pragma unroll 1
       for (int qt = 0; qt < 2; ++qt) {
         const int row = qt * 128 + r_in;                 // the CLS query (row N): raw sum, scaled by cls_grad_finalize_kernel
@@ -489,6 +521,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           drain_row(DQ_COL + 64 * qt, q_scale, base_row + (long long)row * (3 * G.D), cls, row < G.N, row == G.N);
       }
       warp_arrive(dq_free, lane);
+      trace_ev(trace, warp == 12 ? lane : 1, 35, gi, 0);    // drain WG: dQ stored
     }
   }
 
@@ -543,11 +576,30 @@ int space_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const 
     attr = true;
   }
   const int grid = G.groups < num_sms() ? G.groups : num_sms();
+  const char* trace_path = getenv("EGOVLP_ATTN_BWD_TRACE");
+  unsigned long long* trace = nullptr;
+  if (trace_path && trace_path[0]) {
+    EGOVLP_CHECK_CUDA(cudaMalloc(&trace, 4001 * sizeof(unsigned long long)));
+    EGOVLP_CHECK_CUDA(cudaMemsetAsync(trace, 0, 4001 * sizeof(unsigned long long), st));
+  }
   space_attn_bwd_tc_kernel<<<grid, THREADS, smem, st>>>(tm_rows, tm_cls, tm_do_rows, tm_do_cls,
                                                         reinterpret_cast<const bf16*>(out),
                                                         reinterpret_cast<const bf16*>(dout), lse,
-                                                        reinterpret_cast<bf16*>(dqkv), dcls, q_scale, G);
+                                                        reinterpret_cast<bf16*>(dqkv), dcls, q_scale, G, trace);
   EGOVLP_CHECK_LAUNCH();
+  if (trace) {                                             // debugging aid: synchronous dump of the timeline
+    static unsigned long long host[4001];
+    EGOVLP_CHECK_CUDA(cudaStreamSynchronize(st));
+    EGOVLP_CHECK_CUDA(cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost));
+    cudaFree(trace);
+    if (FILE* f = fopen(trace_path, "w")) {
+      const unsigned long long n = host[0] < 4000 ? host[0] : 4000;
+      for (unsigned long long i = 0; i < n; ++i)
+        fprintf(f, "%llu %llu %llu %llu\n", host[1 + i] >> 56, (host[1 + i] >> 48) & 0xff, (host[1 + i] >> 44) & 0xf,
+                host[1 + i] & 0xfffffffffffull);
+      fclose(f);
+    }
+  }
   return EGOVLP_OK;
 }
 
