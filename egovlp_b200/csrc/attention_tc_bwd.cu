@@ -15,12 +15,12 @@
 //   warp 1     MMA issuer (one thread): S and dP of the next step are issued as soon as the softmax warps have pulled the
 //              current ones out of TMEM; dV after P is in smem, dK / dQ after dS
 //   warp 2     TMEM allocator: 512 columns = S 128 | dP 128 | dQ_0 64 | dQ_1 64 | dK 64 | dV 64
-//   warps 4-11 softmax: two threads per query row (64 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) ->
+//   warps 4-19 softmax: four threads per query row (32 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) ->
 //              smem (packed FFMA2 + MUFU, no predicates on the dense first key tile), dS = P (dP - delta) -> smem
-//   warps 12-15 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
+//   warps 20-23 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
 //              buffered), and the accumulator drains (dK / dV per key tile, dQ per group) straight to dqkv as 64-byte row
 //              pieces, CLS-row gradients by fp32 atomics -- so the softmax warps never wait for a drain or a prologue.
-// setmaxnreg splits the register file 72 / 176 / 88 per thread between the control, softmax and drain warpgroups.
+// setmaxnreg splits the register file 72 / 88 / 88 per thread between the control, softmax (16 warps) and drain warpgroups.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,7 +38,7 @@ constexpr int NSLOT = 6;
 constexpr int PB_BYTES = 2 * 128 * ROWB;              // [2 key blocks of 64][128 query rows][128 B]
 constexpr int KBLK_BYTES = 128 * ROWB;                // one 64-key block
 constexpr int LSD_FLOATS = 2 * 2 * TILE_ROWS;         // [parity][lse2 | delta][row]
-constexpr int THREADS = 512;                          // warpgroups: control (TMA / MMA / TMEM) | softmax x2 | drain
+constexpr int THREADS = 768;                          // warpgroups: control (TMA / MMA / TMEM) | softmax x4 | drain
 constexpr int S_COL = 0, DP_COL = 128, DQ_COL = 256, DK_COL = 384, DV_COL = 448;
 
 struct BwdGeom {
@@ -67,11 +67,20 @@ __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
 
 // Optional timeline (EGOVLP_ATTN_BWD_TRACE=<file>): CTA 0 stamps (event, group, step, clock) of its first groups into a
 // device buffer that the host dumps after the launch -- the tool the pipeline of this kernel was tuned with.
-__device__ __forceinline__ void trace_ev(unsigned long long* tr, int lane, int ev, int gi, int it) {
-  if (tr != nullptr && blockIdx.x == 0 && lane == 0 && gi < 6) {
-    const unsigned long long slot = atomicAdd(tr, 1ull);
-    if (slot < 4000) tr[1 + slot] = ((unsigned long long)(ev & 0xff) << 56) | ((unsigned long long)(gi & 0xff) << 48) |
-                                    ((unsigned long long)(it & 0xf) << 44) | (clock64() & 0xfffffffffffull);
+struct Tracer {                                          // per-role private cursor: plain stores, no atomics
+  unsigned long long* p;
+  int n;
+};
+__device__ __forceinline__ Tracer make_tracer(unsigned long long* tr, int role, bool on) {
+  Tracer t;
+  t.p = (tr != nullptr && blockIdx.x == 0 && on) ? tr + 1 + role * 1000 : nullptr;
+  t.n = 0;
+  return t;
+}
+__device__ __forceinline__ void trace_ev(Tracer& t, int ev, int gi, int it) {
+  if (t.p != nullptr && t.n < 1000) {
+    t.p[t.n++] = ((unsigned long long)(ev & 0xff) << 56) | ((unsigned long long)(gi & 0xff) << 48) |
+                 ((unsigned long long)(it & 0xf) << 44) | (clock64() & 0xfffffffffffull);
   }
 }
 
@@ -88,36 +97,35 @@ struct SoftmaxArgs {
   int col0, ncol, vis_cols, lane;
   uint32_t parity, s_full, s_free, p_freeb, p_ready, dp_full, ds_freeb;
   bool active;
-  unsigned long long* trace;
-  int gi, it, tl;                                        // trace: group, step, lane id to stamp with (0 on one warp only)
+  Tracer* trc;
+  int gi, it;
 };
 
 // One (key tile, query tile) step of a softmax thread: S (TMEM) -> P = exp2(S log2e - lse2) -> bf16 smem, then
-// dP (TMEM) -> dS = P (dP - delta) -> bf16 smem.  MASKED = the short second key tile (<= 40 columns per thread, CLS key
-// and padding keys masked per element); the first key tile is dense: 64 columns, packed FFMA2 / FMUL2 / FADD2 math and no
-// predicates (the first profile of this kernel was instruction-issue bound: 12 instructions per element in this loop).
+// dP (TMEM) -> dS = P (dP - delta) -> bf16 smem.  Four threads share a query row, 32 key columns each (fewer in the short
+// second key tile).  MASKED = that second tile (CLS key and padding keys masked per element); the first key tile is
+// dense: packed FFMA2 / FMUL2 / FADD2 math and no predicates (the first profile of this kernel was instruction-issue
+// bound at 12 instructions per element; the second one MUFU / TMEM-read bound on 8 softmax warps -- hence 16 warps).
 template <bool MASKED>
 __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
-  constexpr int NCH = MASKED ? 5 : 8;                    // 8-column chunks handled by a thread
   const f32x2 nl2 = pk2(-A.lse2, -A.lse2), l2e = pk2(LOG2E, LOG2E), ndel = pk2(-A.delta, -A.delta);
   mbar_wait(A.s_full, A.parity);
   tc_fence_after();
-  trace_ev(A.trace, A.tl, 20, A.gi, A.it);               // softmax: s_full seen
+  trace_ev(*A.trc, 20, A.gi, A.it);               // softmax: s_full seen
   mbar_wait(A.p_freeb, A.parity ^ 1);                    // the previous step's dV has consumed the P buffer (long ago)
   {
-    uint32_t sv[64];
+    uint32_t sv[32];
     if (A.active) {
-      // always two wide loads (columns past ncol are stale TMEM, never used): narrow tcgen05.ld shapes pay a fixed
+      // always one wide load (columns past ncol are stale TMEM, never used): narrow tcgen05.ld shapes pay a fixed
       // per-instruction cost that dominated the first version of this kernel
       tmem_ld32(A.s_addr, sv);
-      tmem_ld32(A.s_addr + 32, sv + 32);
       tmem_ld_wait();
     }
     warp_arrive(A.s_free, A.lane);
-    trace_ev(A.trace, A.tl, 21, A.gi, A.it);             // softmax: S in registers
+    trace_ev(*A.trc, 21, A.gi, A.it);             // softmax: S in registers
     if (A.active) {
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) {
+      for (int c = 0; c < 4; ++c) {
         if (!MASKED || 8 * c < A.ncol) {
           uint32_t pk[4];
 #pragma unroll
@@ -140,36 +148,32 @@ __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
   }
   fence_proxy_async_smem();                              // generic-proxy stores -> visible to the UMMA reads
   warp_arrive(A.p_ready, A.lane);
-  trace_ev(A.trace, A.tl, 22, A.gi, A.it);               // softmax: P written
-  // dP -> dS = P (dP - delta), 32 columns at a time; P is read back from this thread's own smem row (bf16, exactly what
-  // dV consumes) instead of being held in 32 registers across the wait.  Masked / padded elements have P == 0 and a
-  // finite dP, so no predicate is needed here.
+  trace_ev(*A.trc, 22, A.gi, A.it);               // softmax: P written
+  // dP -> dS = P (dP - delta); P is read back from this thread's own smem row (bf16, exactly what dV consumes) instead of
+  // being held in registers across the wait.  Masked / padded elements have P == 0 and a finite dP: no predicate here.
   mbar_wait(A.dp_full, A.parity);
   tc_fence_after();
   mbar_wait(A.ds_freeb, A.parity ^ 1);                   // the previous step's dK / dQ have consumed the dS buffer
-  trace_ev(A.trace, A.tl, 23, A.gi, A.it);               // softmax: dp_full + ds_free seen
+  trace_ev(*A.trc, 23, A.gi, A.it);               // softmax: dp_full + ds_free seen
+  if (A.active) {
+    uint32_t dp[32];
+    tmem_ld32(A.dp_addr, dp);
+    tmem_ld_wait();
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    if (A.active && (!MASKED || 32 * hh < A.ncol)) {
-      uint32_t dp[32];
-      tmem_ld32(A.dp_addr + 32 * hh, dp);
-      tmem_ld_wait();
+    for (int c = 0; c < 4; ++c) {
+      if (!MASKED || 8 * c < A.ncol) {
+        const int col = A.col0 + 8 * c;
+        const uint32_t off = (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4);
+        uint32_t pk[4], dsp[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(A.p_row + off));
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (4 * hh + c < NCH && (!MASKED || 32 * hh + 8 * c < A.ncol)) {
-          const int col = A.col0 + 32 * hh + 8 * c;
-          const uint32_t off = (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4);
-          uint32_t pk[4], dsp[4];
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(A.p_row + off));
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float d0, d1;
-            up2(mul2(pk2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)),
-                     add2(pk2(__uint_as_float(dp[8 * c + 2 * j]), __uint_as_float(dp[8 * c + 2 * j + 1])), ndel)), d0, d1);
-            dsp[j] = pack_bf16x2(d0, d1);
-          }
-          st_shared_v4(A.ds_row + off, dsp[0], dsp[1], dsp[2], dsp[3]);
+        for (int j = 0; j < 4; ++j) {
+          float d0, d1;
+          up2(mul2(pk2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)),
+                   add2(pk2(__uint_as_float(dp[8 * c + 2 * j]), __uint_as_float(dp[8 * c + 2 * j + 1])), ndel)), d0, d1);
+          dsp[j] = pack_bf16x2(d0, d1);
         }
+        st_shared_v4(A.ds_row + off, dsp[0], dsp[1], dsp[2], dsp[3]);
       }
     }
   }
@@ -229,13 +233,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(tile_full + 8 * i, 1); mbar_init(tile_empty + 8 * i, 1); }
-    mbar_init(s_full, 1);   mbar_init(s_free, 8);
-    mbar_init(dp_full, 1);  mbar_init(dp_free, 8);
-    mbar_init(p_ready, 8);  mbar_init(p_freeb, 1);
-    mbar_init(ds_ready, 8); mbar_init(ds_freeb, 1);
+    mbar_init(s_full, 1);   mbar_init(s_free, 16);
+    mbar_init(dp_full, 1);  mbar_init(dp_free, 16);
+    mbar_init(p_ready, 16); mbar_init(p_freeb, 1);
+    mbar_init(ds_ready, 16); mbar_init(ds_freeb, 1);
     mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
     mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
-    mbar_init(lsd_ready, 4); mbar_init(lsd_taken, 8);
+    mbar_init(lsd_ready, 4); mbar_init(lsd_taken, 16);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -246,12 +250,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t tmem = *tmem_slot_ptr;
   const int ksteps1 = G.W1 / 16;                        // contraction steps over the second (short) tile
 
-  // register budget: the three single-thread roles give registers back, the softmax warps take them (launch: 128 each; control 72, drain 88, softmax 176)
+  // register budget: the three single-thread roles give registers back, the softmax warps take them (launch: 80 each; control 72, softmax 88, drain 88)
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
+      Tracer trc = make_tracer(trace, 0, true);
       int gi = 0;
       for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
         const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
@@ -259,7 +264,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         for (int j = 0; j < 4; ++j) {                    // Q, K, dO, V
           const int c = 4 * gi + j, slot = c % NSLOT, u = c / NSLOT;
           mbar_wait(tile_empty + 8 * slot, (u & 1) ^ 1);
-          trace_ev(trace, 0, 1, gi, j);                    // TMA: tile j issued
+          trace_ev(trc, 1, gi, j);                    // TMA: tile j issued
           const uint32_t fb = tile_full + 8 * slot, dst = base + slot * TILE_BYTES;
           mbar_expect_tx(fb, (uint32_t)G.NK * ROWB);
           if (j == 2) {
@@ -279,6 +284,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     const uint32_t idesc_s1 = make_idesc_bf16(128, G.W1, false, false);
     constexpr uint32_t idesc_kv = make_idesc_bf16(128, HD, true, true);      // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
     constexpr uint32_t idesc_q = make_idesc_bf16(128, HD, false, true);      // A = dS (K-major), B = K (MN-major)
+    Tracer trc = make_tracer(trace, 1, lane == 0);
     int gi = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
       const int c0 = 4 * gi;
@@ -315,13 +321,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         mbar_wait(tile_full + 8 * ((c0 + 1) % NSLOT), ((c0 + 1) / NSLOT) & 1);
         mbar_wait(s_free, (n & 1) ^ 1);
         tc_fence_after();
-        trace_ev(trace, lane, 10, gi, 0);                 // MMA: S(0) issue
+        trace_ev(trc, 10, gi, 0);                 // MMA: S(0) issue
         issue_s(0);
         mbar_wait(tile_full + 8 * ((c0 + 2) % NSLOT), ((c0 + 2) / NSLOT) & 1);
         mbar_wait(tile_full + 8 * ((c0 + 3) % NSLOT), ((c0 + 3) / NSLOT) & 1);
         mbar_wait(dp_free, (n & 1) ^ 1);
         tc_fence_after();
-        trace_ev(trace, lane, 11, gi, 0);                 // MMA: dP(0) issue
+        trace_ev(trc, 11, gi, 0);                 // MMA: dP(0) issue
         issue_dp(0);
       }
 #pragma unroll 1
@@ -331,10 +337,10 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const int ks_k = kt ? ksteps1 : 8;               // contraction over this key tile's rows
         // ---- dV[kt] (+)= P^T dO
         mbar_wait(p_ready, n & 1);
-        trace_ev(trace, lane, 12, gi, it);                // MMA: p_ready seen
+        trace_ev(trc, 12, gi, it);                // MMA: p_ready seen
         if (qt == 0) mbar_wait(dkv_free, ((2 * gi + kt) & 1) ^ 1);       // previous key tile's dK / dV drained
         tc_fence_after();
-        trace_ev(trace, lane, 13, gi, it);                // MMA: dV issue
+        trace_ev(trc, 13, gi, it);                // MMA: dV issue
         if (lane == 0) {
           for (int j = 0; j < ks_q; ++j)
             umma_bf16_ss(tmem + DV_COL, make_smem_desc_sw128(sP + j * 2048, KBLK_BYTES, 1024),
@@ -342,19 +348,20 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           umma_commit(p_freeb);
         }
         __syncwarp();
+        trace_ev(trc, 16, gi, it);                // MMA: dV issued
         // ---- S of the next step as soon as the current S has left TMEM
         if (it < 3) {
           mbar_wait(s_free, ((n + 1) & 1) ^ 1);
           tc_fence_after();
-          trace_ev(trace, lane, 10, gi, it + 1);
+          trace_ev(trc, 10, gi, it + 1);
           issue_s(it + 1);
         }
         // ---- dK[kt] (+)= dS^T Q,  dQ[qt] (+)= dS K
         mbar_wait(ds_ready, n & 1);
-        trace_ev(trace, lane, 14, gi, it);                // MMA: ds_ready seen
+        trace_ev(trc, 14, gi, it);                // MMA: ds_ready seen
         if (it == 0) mbar_wait(dq_free, (gi & 1) ^ 1);                   // previous group's dQ drained
         tc_fence_after();
-        trace_ev(trace, lane, 15, gi, it);                // MMA: dK / dQ issue
+        trace_ev(trc, 15, gi, it);                // MMA: dK / dQ issue
         if (lane == 0) {
           for (int j = 0; j < ks_q; ++j)
             umma_bf16_ss(tmem + DK_COL, make_smem_desc_sw128(sDS + j * 2048, KBLK_BYTES, 1024),
@@ -371,22 +378,26 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           }
         }
         __syncwarp();
+        trace_ev(trc, 17, gi, it);                // MMA: dK / dQ issued
         if (it < 3) {
           mbar_wait(dp_free, ((n + 1) & 1) ^ 1);
           tc_fence_after();
-          trace_ev(trace, lane, 11, gi, it + 1);
+          trace_ev(trc, 11, gi, it + 1);
           issue_dp(it + 1);
         }
       }
     }
   }
-  } else if (warp < 12) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+  } else if (warp < 20) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ============================== softmax / dS ==============================
-    const int qd = warp & 3, hf = (warp - 4) >> 2;
+    const int qd = warp & 3, qr = (warp - 4) >> 2;       // TMEM lane quadrant, column quarter
     const int r_in = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const int half1 = ((G.W1 / 8 + 1) / 2) * 8;          // columns of half 0 in the short key tile (multiple of 8)
+    // the short key tile's W1 / 8 chunks of 8 columns are dealt to the four quarters as evenly as possible
+    const int ch_base = (G.W1 / 8) / 4, ch_rem = (G.W1 / 8) % 4;
+    const int my_ch1 = ch_base + (qr < ch_rem ? 1 : 0), my_c01 = 8 * (qr * ch_base + min(qr, ch_rem));
+    Tracer trc = make_tracer(trace, 2, warp == 4 && lane == 0);
     int gi = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
       const int f = g % G.T;
@@ -403,8 +414,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const bool rvalid = row < G.NK;
         // keys this query may attend: all NK, except the CLS query outside frame 0 (no CLS key)
         const int nvis = rvalid ? ((row == G.N && f != 0) ? G.N : G.NK) : 0;
-        const int ncol = kt ? (hf ? G.W1 - half1 : half1) : 64;     // this thread's columns of the key tile
-        const int col0 = kt ? hf * half1 : hf * 64;
+        const int ncol = kt ? 8 * my_ch1 : 32;           // this thread's columns of the key tile
+        const int col0 = kt ? my_c01 : qr * 32;
         // invalid (padding) rows: lse2 = +inf makes every P of the row exp2(-inf) = 0, hence dS = 0, without a mask
         SoftmaxArgs sa;
         sa.lse2 = rvalid ? lse2_s[row] : INFINITY;
@@ -422,17 +433,17 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         sa.parity = n & 1;
         sa.s_full = s_full; sa.s_free = s_free; sa.p_freeb = p_freeb; sa.p_ready = p_ready;
         sa.dp_full = dp_full; sa.ds_freeb = ds_freeb;
-        sa.trace = trace; sa.gi = gi; sa.it = it; sa.tl = warp == 4 ? lane : 1;
+        sa.trc = &trc; sa.gi = gi; sa.it = it;
         if (kt == 0) softmax_step<false>(sa);
         else softmax_step<true>(sa);
         fence_proxy_async_smem();
         warp_arrive(dp_free, lane);
         if (lane == 0) mbar_arrive(ds_ready);            // (ordered after the fences + __syncwarp of warp_arrive)
-        trace_ev(trace, sa.tl, 24, gi, it);               // softmax: dS written
+        trace_ev(trc, 24, gi, it);               // softmax: dS written
       }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     // ============================== drain warpgroup ==============================
     // (1) per-row lse (log2 units) and delta = rowsum(dO o O) of the NEXT group, straight from global memory (so it
     //     does not wait for the TMA ring), double-buffered by group parity; (2) the accumulator drains: dK / dV after
@@ -441,7 +452,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     const int qd = warp & 3;
     const int r_in = qd * 32 + lane;                     // TMEM lane = accumulator row owned by this thread
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const int t128 = threadIdx.x - 384;                  // 0..127
+    const int t128 = threadIdx.x - 640;                  // 0..127
+    Tracer trc = make_tracer(trace, 3, warp == 20 && lane == 0);
 
     auto prepare_rows = [&](int g, int par) {
       const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
@@ -492,9 +504,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       // has already drained, i.e. every softmax warp is past it
       if (g + (int)gridDim.x < G.groups) {
         mbar_wait(lsd_taken, gi & 1);                    // every softmax warp has seen phase gi of lsd_ready
-        trace_ev(trace, warp == 12 ? lane : 1, 30, gi, 0);
+        trace_ev(trc, 30, gi, 0);
         prepare_rows(g + gridDim.x, (gi + 1) & 1);
-        trace_ev(trace, warp == 12 ? lane : 1, 31, gi, 0);  // drain WG: next group's lse / delta ready
+        trace_ev(trc, 31, gi, 0);  // drain WG: next group's lse / delta ready
       }
       bf16* base_row = dqkv + ((long long)b * G.S + 1 + f * G.N) * (3 * G.D) + h * HD;
       float* cls = dcls + ((long long)(b * G.H + h) * 3) * HD;
@@ -502,18 +514,18 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       for (int kt = 0; kt < 2; ++kt) {
         mbar_wait(dkv_full, (2 * gi + kt) & 1);
         tc_fence_after();
-        trace_ev(trace, warp == 12 ? lane : 1, 32, gi, kt);  // drain WG: dkv_full seen
+        trace_ev(trc, 32, gi, kt);  // drain WG: dkv_full seen
         const int key = kt * 128 + r_in;
         if (!(kt == 1 && qd * 32 >= G.W1)) {
           drain_row(DK_COL, 1.f, base_row + (long long)key * (3 * G.D) + G.D, cls + HD, key < G.N, key == G.N);
           drain_row(DV_COL, 1.f, base_row + (long long)key * (3 * G.D) + 2 * G.D, cls + 2 * HD, key < G.N, key == G.N);
         }
         warp_arrive(dkv_free, lane);
-        trace_ev(trace, warp == 12 ? lane : 1, 33, gi, kt);  // drain WG: dK / dV stored
+        trace_ev(trc, 33, gi, kt);  // drain WG: dK / dV stored
       }
       mbar_wait(dq_full, gi & 1);
       tc_fence_after();
-      trace_ev(trace, warp == 12 ? lane : 1, 34, gi, 0);    // drain WG: dq_full seen
+      trace_ev(trc, 34, gi, 0);    // drain WG: dq_full seen
 #pragma unroll 1
       for (int qt = 0; qt < 2; ++qt) {
         const int row = qt * 128 + r_in;                 // the CLS query (row N): raw sum, scaled by cls_grad_finalize_kernel
@@ -521,7 +533,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           drain_row(DQ_COL + 64 * qt, q_scale, base_row + (long long)row * (3 * G.D), cls, row < G.N, row == G.N);
       }
       warp_arrive(dq_free, lane);
-      trace_ev(trace, warp == 12 ? lane : 1, 35, gi, 0);    // drain WG: dQ stored
+      trace_ev(trc, 35, gi, 0);    // drain WG: dQ stored
     }
   }
 
@@ -593,10 +605,10 @@ int space_attn_bwd_tc(const void* qkv, const void* out, const void* dout, const 
     EGOVLP_CHECK_CUDA(cudaMemcpy(host, trace, sizeof(host), cudaMemcpyDeviceToHost));
     cudaFree(trace);
     if (FILE* f = fopen(trace_path, "w")) {
-      const unsigned long long n = host[0] < 4000 ? host[0] : 4000;
-      for (unsigned long long i = 0; i < n; ++i)
-        fprintf(f, "%llu %llu %llu %llu\n", host[1 + i] >> 56, (host[1 + i] >> 48) & 0xff, (host[1 + i] >> 44) & 0xf,
-                host[1 + i] & 0xfffffffffffull);
+      for (int i = 0; i < 4000; ++i)
+        if (host[1 + i])
+          fprintf(f, "%llu %llu %llu %llu\n", host[1 + i] >> 56, (host[1 + i] >> 48) & 0xff, (host[1 + i] >> 44) & 0xf,
+                  host[1 + i] & 0xfffffffffffull);
       fclose(f);
     }
   }

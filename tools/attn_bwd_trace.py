@@ -28,7 +28,7 @@ ops.divided_attn_bwd(qkv, o, dout, lse, B, T, N, H, 1, 0.125, dqkv)
 torch.cuda.synchronize()
 del os.environ["EGOVLP_ATTN_BWD_TRACE"]
 NAMES = {1: "TMA   tile issued", 10: "MMA   S issue", 11: "MMA   dP issue", 12: "MMA   p_ready seen", 13: "MMA   dV issue",
-         14: "MMA   ds_ready seen", 15: "MMA   dK/dQ issue", 20: "SOFT  s_full seen", 21: "SOFT  S in regs",
+         14: "MMA   ds_ready seen", 15: "MMA   dK/dQ issue", 16: "MMA   dV issued", 17: "MMA   dK/dQ issued", 20: "SOFT  s_full seen", 21: "SOFT  S in regs",
          22: "SOFT  P written", 23: "SOFT  dp_full seen", 24: "SOFT  dS written", 30: "DRAIN prepare start",
          31: "DRAIN prepare done", 32: "DRAIN dkv_full seen", 33: "DRAIN dK/dV stored", 34: "DRAIN dq_full seen",
          35: "DRAIN dQ stored"}
