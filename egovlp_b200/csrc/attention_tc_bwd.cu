@@ -20,7 +20,7 @@
 //   warps 20-23 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
 //              buffered), and the accumulator drains (dK / dV per key tile, dQ per group) straight to dqkv as 64-byte row
 //              pieces, CLS-row gradients by fp32 atomics -- so the softmax warps never wait for a drain or a prologue.
-// setmaxnreg splits the register file 72 / 88 / 88 per thread between the control, softmax (16 warps) and drain warpgroups.
+// setmaxnreg splits the CTA's registers 56 / 88 / 72 per thread between the control, softmax (16 warps) and drain warpgroups.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -56,12 +56,13 @@ __device__ __forceinline__ void st_shared_v4(uint32_t a, uint32_t x, uint32_t y,
 // showed up as 18 M instructions each for the TMA and the MMA warp in the first profile of this kernel).
 __device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  for (int outer = 0; outer < (1 << 22); ++outer) {
+  const long long t0 = clock64();
+  for (;;) {
 #pragma unroll 1
     for (int i = 0; i < 1024; ++i)
       if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s.  No printf: a call site makes every live register spill around it
   }
-  __trap();        // no printf here: a call site in the wait makes every live register of the caller spill around it
 }
 #define mbar_wait mbar_wait_hot
 
@@ -250,9 +251,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t tmem = *tmem_slot_ptr;
   const int ksteps1 = G.W1 / 16;                        // contraction steps over the second (short) tile
 
-  // register budget: the three single-thread roles give registers back, the softmax warps take them (launch: 80 each; control 72, softmax 88, drain 88)
+  // register budget: the three single-thread roles give registers back, the softmax warps take them (the CTA keeps its launch allocation of 768 x 80: control 56, softmax 88, drain 72 -- setmaxnreg can only hand out what the CTA itself released)
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -443,7 +444,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // ============================== drain warpgroup ==============================
     // (1) per-row lse (log2 units) and delta = rowsum(dO o O) of the NEXT group, straight from global memory (so it
     //     does not wait for the TMA ring), double-buffered by group parity; (2) the accumulator drains: dK / dV after
@@ -464,19 +465,22 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const long long tok = (long long)b * G.S + (row < G.N ? 1 + f * G.N + row : 0);
         const uint4* orow = reinterpret_cast<const uint4*>(out + tok * G.D + h * HD);
         const uint4* drow = reinterpret_cast<const uint4*>(dout + tok * G.D + h * HD);
-        uint4 ov[8], dv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { ov[i] = __ldg(orow + i); dv[i] = __ldg(drow + i); }
         const float l = __ldg(lse_in + ((long long)(b * G.H + h)) * G.S + (row < G.N ? 1 + f * G.N + row : 0));
         float d = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint32_t ou[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w}, du[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+        for (int hh = 0; hh < 2; ++hh) {                   // 64 B of O and dO at a time (72 registers per thread here)
+          uint4 ov[4], dv[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 a = unpack_bf16x2(ou[k]), bb = unpack_bf16x2(du[k]);
-            d = fmaf(a.x, bb.x, d);
-            d = fmaf(a.y, bb.y, d);
+          for (int i = 0; i < 4; ++i) { ov[i] = __ldg(orow + 4 * hh + i); dv[i] = __ldg(drow + 4 * hh + i); }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t ou[4] = {ov[i].x, ov[i].y, ov[i].z, ov[i].w}, du[4] = {dv[i].x, dv[i].y, dv[i].z, dv[i].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 a = unpack_bf16x2(ou[k]), bb = unpack_bf16x2(du[k]);
+              d = fmaf(a.x, bb.x, d);
+              d = fmaf(a.y, bb.y, d);
+            }
           }
         }
         lse2_s[row] = l * LOG2E;
