@@ -348,13 +348,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue = {}
+
     def timed(n, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
+        t0 = time.perf_counter()
         for _ in range(n):
             out = fn()
+        host_enqueue["ms_per_step"] = (time.perf_counter() - t0) * 1e3 / n     # CPU time to ENQUEUE a step (no sync inside)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -370,6 +374,7 @@ def main():
     _lib.reset_launch_count()
     ops.profile(True)
     ms_total, out = timed(args.steps, lambda: step(resident))
+    enqueue_ms = host_enqueue["ms_per_step"]
     prof = ops.profile(False)
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -475,7 +480,10 @@ def main():
                              "launches_per_step": g_calls / args.steps, "share_of_step": g_ms / ms_total,
                              "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)"},
                 "roofline_hbm": hbm, "roofline_hbm_peak_source": peak_src + ", copy bandwidth",
-                "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "host_enqueue_ms_per_step": enqueue_ms,
+                "host_enqueue_note": "CPU wall time to issue one step's ctypes C-ABI calls (profiling events included); "
+                                     "the step is GPU-bound while this stays below ms_per_step"}
         if trainer_seq is not None:
             line["trainer_sequence"] = trainer_seq
         line.update(extra)

@@ -15,12 +15,13 @@
 //   warp 1     MMA issuer (one thread): S and dP of the next step are issued as soon as the softmax warps have pulled the
 //              current ones out of TMEM; dV after P is in smem, dK / dQ after dS
 //   warp 2     TMEM allocator: 512 columns = S 128 | dP 128 | dQ_0 64 | dQ_1 64 | dK 64 | dV 64
-//   warps 4-19 softmax: four threads per query row (32 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) ->
+//   warps 4-11 softmax: two threads per query row (64 key columns each): TMEM -> registers, P = exp2(S log2e - lse2) ->
 //              smem (packed FFMA2 + MUFU, no predicates on the dense first key tile), dS = P (dP - delta) -> smem
-//   warps 20-23 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
+//   warps 12-15 drain warpgroup: per-row lse2 / delta = rowsum(dO o O) of the NEXT group from global memory (double
 //              buffered), and the accumulator drains (dK / dV per key tile, dQ per group) straight to dqkv as 64-byte row
 //              pieces, CLS-row gradients by fp32 atomics -- so the softmax warps never wait for a drain or a prologue.
-// setmaxnreg splits the CTA's registers 56 / 88 / 72 per thread between the control, softmax (16 warps) and drain warpgroups.
+// setmaxnreg splits the CTA's registers 72 / 176 / 88 per thread between the control, softmax and drain warpgroups.
+// (16 softmax warps -- four threads per row -- were measured SLOWER: 1.82 ms vs 1.46 ms at B = 64.)
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,7 +39,7 @@ constexpr int NSLOT = 6;
 constexpr int PB_BYTES = 2 * 128 * ROWB;              // [2 key blocks of 64][128 query rows][128 B]
 constexpr int KBLK_BYTES = 128 * ROWB;                // one 64-key block
 constexpr int LSD_FLOATS = 2 * 2 * TILE_ROWS;         // [parity][lse2 | delta][row]
-constexpr int THREADS = 768;                          // warpgroups: control (TMA / MMA / TMEM) | softmax x4 | drain
+constexpr int THREADS = 512;                          // warpgroups: control (TMA / MMA / TMEM) | softmax x2 | drain
 constexpr int S_COL = 0, DP_COL = 128, DQ_COL = 256, DK_COL = 384, DV_COL = 448;
 
 struct BwdGeom {
@@ -103,30 +104,31 @@ struct SoftmaxArgs {
 };
 
 // One (key tile, query tile) step of a softmax thread: S (TMEM) -> P = exp2(S log2e - lse2) -> bf16 smem, then
-// dP (TMEM) -> dS = P (dP - delta) -> bf16 smem.  Four threads share a query row, 32 key columns each (fewer in the short
-// second key tile).  MASKED = that second tile (CLS key and padding keys masked per element); the first key tile is
-// dense: packed FFMA2 / FMUL2 / FADD2 math and no predicates (the first profile of this kernel was instruction-issue
-// bound at 12 instructions per element; the second one MUFU / TMEM-read bound on 8 softmax warps -- hence 16 warps).
+// dP (TMEM) -> dS = P (dP - delta) -> bf16 smem.  MASKED = the short second key tile (<= 40 columns per thread, CLS key
+// and padding keys masked per element); the first key tile is dense: 64 columns, packed FFMA2 / FMUL2 / FADD2 math and no
+// predicates (the first profile of this kernel was instruction-issue bound: 12 instructions per element in this loop).
 template <bool MASKED>
 __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
+  constexpr int NCH = MASKED ? 5 : 8;                    // 8-column chunks handled by a thread
   const f32x2 nl2 = pk2(-A.lse2, -A.lse2), l2e = pk2(LOG2E, LOG2E), ndel = pk2(-A.delta, -A.delta);
   mbar_wait(A.s_full, A.parity);
   tc_fence_after();
   trace_ev(*A.trc, 20, A.gi, A.it);               // softmax: s_full seen
   mbar_wait(A.p_freeb, A.parity ^ 1);                    // the previous step's dV has consumed the P buffer (long ago)
   {
-    uint32_t sv[32];
+    uint32_t sv[64];
     if (A.active) {
-      // always one wide load (columns past ncol are stale TMEM, never used): narrow tcgen05.ld shapes pay a fixed
+      // always two wide loads (columns past ncol are stale TMEM, never used): narrow tcgen05.ld shapes pay a fixed
       // per-instruction cost that dominated the first version of this kernel
       tmem_ld32(A.s_addr, sv);
+      tmem_ld32(A.s_addr + 32, sv + 32);
       tmem_ld_wait();
     }
     warp_arrive(A.s_free, A.lane);
     trace_ev(*A.trc, 21, A.gi, A.it);             // softmax: S in registers
     if (A.active) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NCH; ++c) {
         if (!MASKED || 8 * c < A.ncol) {
           uint32_t pk[4];
 #pragma unroll
@@ -150,31 +152,35 @@ __device__ __forceinline__ void softmax_step(const SoftmaxArgs& A) {
   fence_proxy_async_smem();                              // generic-proxy stores -> visible to the UMMA reads
   warp_arrive(A.p_ready, A.lane);
   trace_ev(*A.trc, 22, A.gi, A.it);               // softmax: P written
-  // dP -> dS = P (dP - delta); P is read back from this thread's own smem row (bf16, exactly what dV consumes) instead of
-  // being held in registers across the wait.  Masked / padded elements have P == 0 and a finite dP: no predicate here.
+  // dP -> dS = P (dP - delta), 32 columns at a time; P is read back from this thread's own smem row (bf16, exactly what
+  // dV consumes) instead of being held in 32 registers across the wait.  Masked / padded elements have P == 0 and a
+  // finite dP, so no predicate is needed here.
   mbar_wait(A.dp_full, A.parity);
   tc_fence_after();
   mbar_wait(A.ds_freeb, A.parity ^ 1);                   // the previous step's dK / dQ have consumed the dS buffer
   trace_ev(*A.trc, 23, A.gi, A.it);               // softmax: dp_full + ds_free seen
-  if (A.active) {
-    uint32_t dp[32];
-    tmem_ld32(A.dp_addr, dp);
-    tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      if (!MASKED || 8 * c < A.ncol) {
-        const int col = A.col0 + 8 * c;
-        const uint32_t off = (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4);
-        uint32_t pk[4], dsp[4];
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(A.p_row + off));
+  for (int hh = 0; hh < 2; ++hh) {
+    if (A.active && (!MASKED || 32 * hh < A.ncol)) {
+      uint32_t dp[32];
+      tmem_ld32(A.dp_addr + 32 * hh, dp);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float d0, d1;
-          up2(mul2(pk2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)),
-                   add2(pk2(__uint_as_float(dp[8 * c + 2 * j]), __uint_as_float(dp[8 * c + 2 * j + 1])), ndel)), d0, d1);
-          dsp[j] = pack_bf16x2(d0, d1);
+      for (int c = 0; c < 4; ++c) {
+        if (4 * hh + c < NCH && (!MASKED || 32 * hh + 8 * c < A.ncol)) {
+          const int col = A.col0 + 32 * hh + 8 * c;
+          const uint32_t off = (col >> 6) * KBLK_BYTES + ((((col & 63) >> 3) ^ A.sw) << 4);
+          uint32_t pk[4], dsp[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(pk[0]), "=r"(pk[1]), "=r"(pk[2]), "=r"(pk[3]) : "r"(A.p_row + off));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float d0, d1;
+            up2(mul2(pk2(__uint_as_float(pk[j] << 16), __uint_as_float(pk[j] & 0xffff0000u)),
+                     add2(pk2(__uint_as_float(dp[8 * c + 2 * j]), __uint_as_float(dp[8 * c + 2 * j + 1])), ndel)), d0, d1);
+            dsp[j] = pack_bf16x2(d0, d1);
+          }
+          st_shared_v4(A.ds_row + off, dsp[0], dsp[1], dsp[2], dsp[3]);
         }
-        st_shared_v4(A.ds_row + off, dsp[0], dsp[1], dsp[2], dsp[3]);
       }
     }
   }
@@ -234,13 +240,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < NSLOT; ++i) { mbar_init(tile_full + 8 * i, 1); mbar_init(tile_empty + 8 * i, 1); }
-    mbar_init(s_full, 1);   mbar_init(s_free, 16);
-    mbar_init(dp_full, 1);  mbar_init(dp_free, 16);
-    mbar_init(p_ready, 16); mbar_init(p_freeb, 1);
-    mbar_init(ds_ready, 16); mbar_init(ds_freeb, 1);
+    mbar_init(s_full, 1);   mbar_init(s_free, 8);
+    mbar_init(dp_full, 1);  mbar_init(dp_free, 8);
+    mbar_init(p_ready, 8);  mbar_init(p_freeb, 1);
+    mbar_init(ds_ready, 8); mbar_init(ds_freeb, 1);
     mbar_init(dkv_full, 1); mbar_init(dkv_free, 4);
     mbar_init(dq_full, 1);  mbar_init(dq_free, 4);
-    mbar_init(lsd_ready, 4); mbar_init(lsd_taken, 16);
+    mbar_init(lsd_ready, 4); mbar_init(lsd_taken, 8);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -251,9 +257,9 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
   const uint32_t tmem = *tmem_slot_ptr;
   const int ksteps1 = G.W1 / 16;                        // contraction steps over the second (short) tile
 
-  // register budget: the three single-thread roles give registers back, the softmax warps take them (the CTA keeps its launch allocation of 768 x 80: control 56, softmax 88, drain 72 -- setmaxnreg can only hand out what the CTA itself released)
+  // register budget: the three single-thread roles give registers back, the softmax warps take them (the CTA keeps its launch allocation of 512 x 128: control 72, softmax 176, drain 88 -- setmaxnreg can only hand out what the CTA itself released)
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
@@ -389,15 +395,13 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       }
     }
   }
-  } else if (warp < 20) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // ============================== softmax / dS ==============================
-    const int qd = warp & 3, qr = (warp - 4) >> 2;       // TMEM lane quadrant, column quarter
+    const int qd = warp & 3, hf = (warp - 4) >> 2;
     const int r_in = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    // the short key tile's W1 / 8 chunks of 8 columns are dealt to the four quarters as evenly as possible
-    const int ch_base = (G.W1 / 8) / 4, ch_rem = (G.W1 / 8) % 4;
-    const int my_ch1 = ch_base + (qr < ch_rem ? 1 : 0), my_c01 = 8 * (qr * ch_base + min(qr, ch_rem));
+    const int half1 = ((G.W1 / 8 + 1) / 2) * 8;          // columns of half 0 in the short key tile (multiple of 8)
     Tracer trc = make_tracer(trace, 2, warp == 4 && lane == 0);
     int gi = 0;
     for (int g = blockIdx.x; g < G.groups; g += gridDim.x, ++gi) {
@@ -415,8 +419,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
         const bool rvalid = row < G.NK;
         // keys this query may attend: all NK, except the CLS query outside frame 0 (no CLS key)
         const int nvis = rvalid ? ((row == G.N && f != 0) ? G.N : G.NK) : 0;
-        const int ncol = kt ? 8 * my_ch1 : 32;           // this thread's columns of the key tile
-        const int col0 = kt ? my_c01 : qr * 32;
+        const int ncol = kt ? (hf ? G.W1 - half1 : half1) : 64;     // this thread's columns of the key tile
+        const int col0 = kt ? hf * half1 : hf * 64;
         // invalid (padding) rows: lse2 = +inf makes every P of the row exp2(-inf) = 0, hence dS = 0, without a mask
         SoftmaxArgs sa;
         sa.lse2 = rvalid ? lse2_s[row] : INFINITY;
@@ -444,7 +448,7 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
       }
     }
   } else {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // ============================== drain warpgroup ==============================
     // (1) per-row lse (log2 units) and delta = rowsum(dO o O) of the NEXT group, straight from global memory (so it
     //     does not wait for the TMA ring), double-buffered by group parity; (2) the accumulator drains: dK / dV after
@@ -453,8 +457,8 @@ space_attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
     const int qd = warp & 3;
     const int r_in = qd * 32 + lane;                     // TMEM lane = accumulator row owned by this thread
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
-    const int t128 = threadIdx.x - 640;                  // 0..127
-    Tracer trc = make_tracer(trace, 3, warp == 20 && lane == 0);
+    const int t128 = threadIdx.x - 384;                  // 0..127
+    Tracer trc = make_tracer(trace, 3, warp == 12 && lane == 0);
 
     auto prepare_rows = [&](int g, int par) {
       const int f = g % G.T, h = (g / G.T) % G.H, b = g / (G.T * G.H);
