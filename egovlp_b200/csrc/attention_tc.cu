@@ -29,6 +29,20 @@ constexpr int P_BYTES = 4 * P_BLOCK_BYTES;
 constexpr int TC_THREADS = 384;             // TMA, MMA, TMEM-alloc, spare + 8 softmax warps
 constexpr int S1_COL = 224, O_COL = 448;  // TMEM columns: S_0 at 0, S_1 at 224, O at 448 (NKP <= 224)
 
+// Bounded mbarrier wait without a printf call site (a call makes every live register of the caller spill around it) and
+// with the clock looked at only every 1024 polls: a waiting warp costs almost no issue slots.
+__device__ __forceinline__ void mbar_wait_hot(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 1024; ++i)
+      if (mbar_try_wait(bar, parity)) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a protocol bug fails the launch instead of hanging the GPU
+  }
+}
+#define mbar_wait mbar_wait_hot
+
 struct TcGeom {
   int B, H, T, N, S, D, NK, NKP, groups;
 };
@@ -187,34 +201,49 @@ space_attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_rows, const __gr
           __syncwarp();
           if (lane == 0) mbar_arrive(sfree_bar + 8);
         }
+        // half 0 holds patch keys only (dense: no predicates, packed FFMA2 / FADD2 math); half 1 ends with the CLS key
+        // and the padding columns (masked per element).  Padding ROWS compute garbage-but-finite values nobody stores.
         float mx = -INFINITY;
+        if (half == 0) {
 #pragma unroll
-        for (int j = 0; j < 112; ++j) {
-          const bool ok = j < ncol && col0 + j < vis;
-          r[j] = ok ? r[j] : 0xff800000u;
-          mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 112; ++j)
+            if (j < ncol) mx = fmaxf(mx, __uint_as_float(r[j]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 112; ++j) {
+            const bool ok = j < ncol && col0 + j < vis;
+            r[j] = ok ? r[j] : 0xff800000u;
+            mx = fmaxf(mx, __uint_as_float(r[j]));
+          }
         }
         xmax[half * 128 + r_in_tile] = mx;
         asm volatile("bar.sync %0, 64;" ::"r"(1 + qd) : "memory");
         mx = fmaxf(mx, xmax[(half ^ 1) * 128 + r_in_tile]);
         const float ms = mx * LOG2E;
+        const f32x2 nms = pk2(-ms, -ms), l2e = pk2(LOG2E, LOG2E);
         mbar_wait(pfree_bar, (n & 1) ^ 1);               // the previous P V product has consumed the P tile
-        float sum = 0.f;
+        f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll
         for (int c = 0; c < 14; ++c) {
           if (8 * c < ncol) {
-            float p[8];
+            uint32_t pk[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              p[j] = exp2f(__uint_as_float(r[8 * c + j]) * LOG2E - ms);
-              sum += p[j];
+            for (int j = 0; j < 4; ++j) {
+              float e0, e1;
+              up2(fma2(pk2(__uint_as_float(r[8 * c + 2 * j]), __uint_as_float(r[8 * c + 2 * j + 1])), l2e, nms), e0, e1);
+              e0 = exp2f(e0);                            // masked entries are -inf -> exp2(-inf) = 0
+              e1 = exp2f(e1);
+              sum2 = add2(sum2, pk2(e0, e1));
+              pk[j] = pack_bf16x2(e0, e1);
             }
             const int col = col0 + 8 * c;
             const uint32_t a = sP + (col >> 6) * P_BLOCK_BYTES + r_in_tile * ROWB + ((((col & 63) >> 3) ^ (r_in_tile & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(p[0], p[1])),
-                         "r"(pack_bf16x2(p[2], p[3])), "r"(pack_bf16x2(p[4], p[5])), "r"(pack_bf16x2(p[6], p[7])));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]));
           }
         }
+        float sum, sum_hi;
+        up2(sum2, sum, sum_hi);
+        sum += sum_hi;
         xsum[half * 128 + r_in_tile] = sum;
         tc_fence_before();
         fence_proxy_async_smem();                        // P (generic-proxy stores) -> visible to the UMMA reads
