@@ -355,10 +355,11 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
-        t0 = time.perf_counter()
-        for _ in range(n):
+        for i in range(n):
+            t0 = time.perf_counter()
             out = fn()
-        host_enqueue["ms_per_step"] = (time.perf_counter() - t0) * 1e3 / n     # CPU time to ENQUEUE a step (no sync inside)
+            if i == 0:   # first step after the synchronisation: the launch queue is empty, so this is pure host time
+                host_enqueue["ms_per_step"] = (time.perf_counter() - t0) * 1e3
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -482,7 +483,7 @@ def main():
                 "roofline_hbm": hbm, "roofline_hbm_peak_source": peak_src + ", copy bandwidth",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "host_enqueue_ms_per_step": enqueue_ms,
-                "host_enqueue_note": "CPU wall time to issue one step's ctypes C-ABI calls (profiling events included); "
+                "host_enqueue_note": "CPU wall time to issue the first timed step's ctypes C-ABI calls into an empty launch queue (profiling events included); "
                                      "the step is GPU-bound while this stays below ms_per_step"}
         if trainer_seq is not None:
             line["trainer_sequence"] = trainer_seq
