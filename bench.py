@@ -253,6 +253,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-ddp-comm", action="store_true", help="diagnostic: DDP no_sync (no gradient all-reduce)")
     ap.add_argument("--ddp-bf16-compress", action="store_true", help="bf16 gradient-compression DDP comm hook")
+    ap.add_argument("--ddp-bucket-mb", type=int, default=0,
+                    help="DDP bucket_cap_mb (default: EGOVLP_DDP_BUCKET_MB or 2048 = ONE gradient bucket all-reduced after "
+                         "the backward; 25 = torch's default overlapped buckets)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.batch = args.batch or wl["batch"]
@@ -288,7 +291,12 @@ def main():
     if not train:
         net.eval()
     elif world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True)
+        # One bucket = one fp32 all-reduce (724 MB, ~2 ms over NVLink / NVSwitch) AFTER the backward: overlapped 25 MB
+        # buckets make NCCL's CTAs compete with the persistent one-CTA-per-SM GEMMs of the backward (whose static tile
+        # schedule then waits for the delayed SMs) and cost more than they hide -- measured, see DESIGN.md section 8.
+        bucket_mb = args.ddp_bucket_mb or int(os.environ.get("EGOVLP_DDP_BUCKET_MB", "2048"))
+        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], gradient_as_bucket_view=True,
+                                                          bucket_cap_mb=bucket_mb)
         if args.ddp_bf16_compress:
             from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
             model.register_comm_hook(None, default_hooks.bf16_compress_hook)
@@ -488,6 +496,8 @@ def main():
         if trainer_seq is not None:
             line["trainer_sequence"] = trainer_seq
         line.update(extra)
+        if world > 1 and train:
+            line["ddp_bucket_cap_mb"] = bucket_mb
         if args.no_ddp_comm or args.ddp_bf16_compress:
             line["ddp_variant"] = "no_sync (diagnostic)" if args.no_ddp_comm else "bf16_compress_hook"
         if world == 1:
