@@ -356,18 +356,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    host_enqueue = {}
-
     def timed(n, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         out = None
-        for i in range(n):
-            t0 = time.perf_counter()
+        for _ in range(n):
             out = fn()
-            if i == 0:   # first step after the synchronisation: the launch queue is empty, so this is pure host time
-                host_enqueue["ms_per_step"] = (time.perf_counter() - t0) * 1e3
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -383,7 +378,6 @@ def main():
     _lib.reset_launch_count()
     ops.profile(True)
     ms_total, out = timed(args.steps, lambda: step(resident))
-    enqueue_ms = host_enqueue["ms_per_step"]
     prof = ops.profile(False)
     launches = _lib.launch_count()
     clocks = sampler.stop() if rank == 0 else None
@@ -490,9 +484,9 @@ def main():
                              "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)"},
                 "roofline_hbm": hbm, "roofline_hbm_peak_source": peak_src + ", copy bandwidth",
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "host_enqueue_ms_per_step": enqueue_ms,
-                "host_enqueue_note": "CPU wall time to issue the first timed step's ctypes C-ABI calls into an empty launch queue (profiling events included); "
-                                     "the step is GPU-bound while this stays below ms_per_step"}
+                # share of the timed region covered by the CUDA-event intervals of the profiled kernels (GEMM + attention +
+                # LayerNorm): close to 1 = the step is GPU-bound, the ~700 ctypes C-ABI calls per step stay ahead of the GPU
+                "gpu_busy_fraction_profiled_kernels": sum(ms for _, ms, _ in prof.values()) / ms_total}
         if trainer_seq is not None:
             line["trainer_sequence"] = trainer_seq
         line.update(extra)
