@@ -38,7 +38,7 @@ struct EpiParams {
   bf16* out2;
   long long ldr, ldaux, ldo, ldo2;
   int out_mode;  // 0 bf16 store, 1 fp32 store, 2 fp32 atomic add
-  int act;       // 0 none, 1 gelu(erf), 2 multiply by gelu'(aux)
+  int act;       // 0 none, 1 gelu(erf), 2 multiply by gelu'(aux), 3 gelu(erf) with out2 = gelu', 4 multiply by aux
   float alpha;
   float col_scale;
   int col_scale_ncols;
@@ -88,6 +88,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   float e;
   const float xq = x * gelu_q(x, e);
   return x >= 0.f ? x - xq : xq;
+}
+// GELU(x) and GELU'(x) = Phi(x) + x phi(x) from ONE evaluation of q (the fc1 epilogue stores the derivative for the
+// backward instead of the pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4)
+__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) {
+  float e;
+  const float q = gelu_q(x, e);
+  const float xq = x * q;
+  g = x >= 0.f ? x - xq : xq;
+  d = fmaf(x * 0.3989422804014327f, e, x >= 0.f ? 1.f - q : q);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
   float e;
@@ -360,17 +369,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= ep.col_scale;
         }
-        if (ep.out2) {
-          stage_bf16_rows(stg, lane, v);
-          __syncwarp();
-          store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
-          __syncwarp();
-        }
-        if (ep.act == 1) {
+        if (ep.act == 3) {                     // out = GELU(v), out2 = GELU'(v)
+          float d[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          for (int j = 0; j < 32; ++j) gelu_and_grad_fast(v[j], v[j], d[j]);
+          if (ep.out2) {
+            stage_bf16_rows(stg, lane, d);
+            __syncwarp();
+            store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
+            __syncwarp();
+          }
+        } else {
+          if (ep.out2) {
+            stage_bf16_rows(stg, lane, v);
+            __syncwarp();
+            store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
+            __syncwarp();
+          }
+          if (ep.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+          }
         }
-        const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.colsum != nullptr;
+        const bool wide = ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.act == 4 || ep.colsum != nullptr;
         if (!wide) {
           stage_bf16_rows(stg, lane, v);
           __syncwarp();
@@ -396,7 +417,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const int rrow = ep.res_row_mod ? grow % ep.res_row_mod : grow;
               resv[i] = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + col));
             }
-            if (ep.act == 2) auxv[i] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
+            if (ep.act == 2 || ep.act == 4) auxv[i] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
           }
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -407,6 +428,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
               const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
               x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
               x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
+            } else if (ep.act == 4) {          // aux already holds GELU'(pre-activation)
+              const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
+              x.x *= p0.x; x.y *= p0.y; x.z *= p1.x; x.w *= p1.y;
             }
             if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
             if (grow < M) {
@@ -517,9 +541,9 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   EGOVLP_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8 (16B TMA strides)");
   EGOVLP_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0,
                    "gemm: operands must be 16B aligned");
-  EGOVLP_CHECK_ARG(e->out_mode >= 0 && e->out_mode <= 2 && e->act >= 0 && e->act <= 2, "gemm: bad epilogue mode");
+  EGOVLP_CHECK_ARG(e->out_mode >= 0 && e->out_mode <= 2 && e->act >= 0 && e->act <= 4, "gemm: bad epilogue mode");
   EGOVLP_CHECK_ARG(split_k <= 1 || e->out_mode == 2, "gemm: split_k > 1 needs out_mode=2 (fp32 atomic accumulate)");
-  EGOVLP_CHECK_ARG(e->act != 2 || e->aux, "gemm: act=2 needs aux");
+  EGOVLP_CHECK_ARG((e->act != 2 && e->act != 4) || e->aux, "gemm: act=2/4 needs aux");
   EGOVLP_CHECK_ARG(e->ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
   EpiParams ep;
   ep.bias = e->bias; ep.residual = e->residual; ep.aux = reinterpret_cast<const bf16*>(e->aux);

@@ -40,14 +40,17 @@ int egovlp_abi_version(void);
  *   b_mn_major = 0: B stored [N, K] (ld = ldb);  1: B stored [K, N] (n contiguous)
  * Epilogue, applied in this order to v = alpha * acc:
  *   v += bias[n];  if (n < col_scale_ncols) v *= col_scale;  out2[m,n] = bf16(v) (if out2);
- *   act 1: v = gelu_erf(v)   act 2: v *= gelu_erf'(aux[m,n]);   v += residual[m,n] (fp32);
+ *   act 1: v = gelu_erf(v)   act 2: v *= gelu_erf'(aux[m,n]);
+ *   act 3: out2[m,n] = bf16(gelu_erf'(v)) (instead of v), then v = gelu_erf(v)   act 4: v *= aux[m,n]
+ *          (3 + 4 = the Mlp pair, model/video_transformer.py:46-52: fc1 saves the GELU derivative, the fc2 input-gradient
+ *          GEMM only multiplies by it);   v += residual[m,n] (fp32);
  *   out_mode 0: out(bf16) = v;  1: out(fp32) = v;  2: atomicAdd(out(fp32), v) (needed for split_k>1)
  * Constraints: N % 32 == 0, lda/ldb/ldo % 8 == 0, 16B-aligned bases.
  */
 typedef struct egovlp_gemm_epilogue {
   const float* bias;     /* [N] fp32 or NULL */
   const float* residual; /* [M, ldr] fp32 or NULL */
-  const void* aux;       /* [M, ldaux] bf16, for act == 2 */
+  const void* aux;       /* [M, ldaux] bf16, for act == 2 / 4 */
   void* out;             /* [M, ldo] bf16 (out_mode 0) or fp32 (1, 2) */
   void* out2;            /* [M, ldo2] bf16 or NULL */
   long long ldr, ldaux, ldo, ldo2;

@@ -99,6 +99,18 @@ def test_gemm_epilogues(ops, gemm_mode):
     ops.gemm(a, b, out16, aux=aux, act=2, colsum=cs)
     assert rel_err(out16, out) < 4e-3
     assert rel_err(cs, 1 + out.sum(0)) < 1e-4
+    # the Mlp pair of the training step: act 3 = GELU with its derivative saved to out2, act 4 = multiply by aux
+    h3, d3 = torch.empty_like(h), torch.empty_like(h)
+    ops.gemm(a, b, h3, bias=bias, act=3, out2=d3)
+    accg = acc.clone().requires_grad_(True)
+    torch.nn.functional.gelu(accg).sum().backward()
+    assert torch.equal(h3, h)
+    assert rel_err(d3, accg.grad) < 4e-3
+    out4 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    cs4 = torch.ones(N, device="cuda")
+    ops.gemm(a, b, out4, aux=d3, act=4, colsum=cs4)
+    ref4 = (a.float() @ b.float().t()) * d3.float()
+    assert rel_err(out4, ref4) < 4e-3 and rel_err(cs4, 1 + ref4.sum(0)) < 1e-4
     # q-scale on the first 256 columns
     out = torch.empty(M, N, device="cuda", dtype=torch.float32)
     ops.gemm(a, b, out, bias=bias, col_scale=0.125, col_scale_ncols=256)
