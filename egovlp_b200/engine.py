@@ -246,6 +246,9 @@ def wgrad_and_bgrad(dy16, x16, n_out, n_in):
 
 
 _WGRAD_COLSUM = os.environ.get("EGOVLP_WGRAD_COLSUM", "1") != "0"
+# Mlp pair: fc1 saves GELU'(pre-activation) (GEMM act 3) and the fc2 input-gradient GEMM multiplies by it (act 4);
+# EGOVLP_GELU_DERIV=0 = the round-1 pair (pre-activation saved, GELU' recomputed in the dgrad epilogue), for A/B runs
+_ACT_FWD, _ACT_BWD = (3, 4) if os.environ.get("EGOVLP_GELU_DERIV", "1") != "0" else (1, 2)
 
 
 def bgrad(dy):
@@ -340,7 +343,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         n2, mean2, rstd2 = ln(sr, n2w, n2b)
         h = _empty((M, HID), BF16, x2)
         u = _empty((M, HID), BF16, x2) if train else None          # GELU'(pre-activation), consumed by the backward
-        ops.gemm(n2, cache.get(f1w), h, bias=f1b.detach(), act=3 if train else 1, out2=u)   # u = GELU'(fc1 output)
+        ops.gemm(n2, cache.get(f1w), h, bias=f1b.detach(), act=_ACT_FWD if train else 1, out2=u)   # u = GELU'(fc1 output)
         y = _empty((M, D), F32, x2)
         ops.gemm(h, cache.get(f2w), y, bias=f2b.detach(), residual=sr)
         if train:
@@ -377,7 +380,7 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         g_f2w = wgrad(dy16, h, D, HID)
         du = _empty((M, HID), BF16, dy)
         g_f1b = _zeros((HID,), dy)
-        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=4, colsum=g_f1b)  # (dy W2) * gelu'; + bias grad
+        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=_ACT_BWD, colsum=g_f1b)  # (dy W2) * gelu'; + bias grad
         g_f1w = wgrad(du, n2, HID, D)
         dn2 = _empty((M, D), BF16, dy)                       # LayerNorm-input gradients travel as bf16
         ops.gemm(du, cache.get(f1w), dn2, b_mn=True)
@@ -525,7 +528,7 @@ class TextTowerFn(torch.autograd.Function):
             m1, r1 = _empty((M,), F32, dev), _empty((M,), F32, dev)
             ops.layernorm_fwd(sa, sw.detach(), sb.detach(), eps, y16=x1_16, y32=x1, mean=m1, rstd=r1)
             hh, u = _empty((M, HID), BF16, dev), (_empty((M, HID), BF16, dev) if train else None)
-            ops.gemm(x1_16, cache.get(l1w), hh, bias=l1b.detach(), act=3 if train else 1, out2=u)
+            ops.gemm(x1_16, cache.get(l1w), hh, bias=l1b.detach(), act=_ACT_FWD if train else 1, out2=u)
             ff = _empty((M, D), F32, dev)
             if p_hid > 0:
                 ops.gemm(hh, cache.get(l2w), ff, bias=l2b.detach())
@@ -597,7 +600,7 @@ class TextTowerFn(torch.autograd.Function):
                 ops.dropout(dff, p_hid, seed, 2 + 2 * li, y32=dffn, y16=dffn16)
             g_l2w, g_l2b = wgrad(dffn16, hh, D, HID), bgrad(dffn)
             du = _empty((M, HID), BF16, dout)
-            ops.gemm(dffn16, cache.get(l2w), du, b_mn=True, aux=u, act=4)
+            ops.gemm(dffn16, cache.get(l2w), du, b_mn=True, aux=u, act=_ACT_BWD)
             g_l1w, g_l1b = wgrad(du, x1_16, HID, D), bgrad(du)
             dx1 = _empty((M, D), F32, dout)
             ops.gemm(du, cache.get(l1w), dx1, b_mn=True, residual=dff)                     # + residual path
