@@ -379,9 +379,8 @@ class SpaceTimeBlockFn(torch.autograd.Function):
         # ---- MLP:  y = sr + fc2(gelu(fc1(LN2(sr))))
         g_f2w = wgrad(dy16, h, D, HID)
         du = _empty((M, HID), BF16, dy)
-        g_f1b = _zeros((HID,), dy)
-        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=_ACT_BWD, colsum=g_f1b)  # (dy W2) * gelu'; + bias grad
-        g_f1w = wgrad(du, n2, HID, D)
+        ops.gemm(dy16, cache.get(f2w), du, b_mn=True, aux=u, act=_ACT_BWD)                # (dy W2) * gelu'
+        g_f1w, g_f1b = wgrad_and_bgrad(du, n2, HID, D)       # fc1 bias gradient = colsum(du), summed inside the wgrad GEMM
         dn2 = _empty((M, D), BF16, dy)                       # LayerNorm-input gradients travel as bf16
         ops.gemm(du, cache.get(f1w), dn2, b_mn=True)
         del du

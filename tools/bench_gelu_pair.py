@@ -33,6 +33,15 @@ for name, fn in (("fc1 plain", lambda: ops.gemm(x, w1, h, bias=b1)),
                  ("fc1 act3 + derivative", lambda: ops.gemm(x, w1, h, bias=b1, act=3, out2=u)),
                  ("dgrad-fc2 plain", lambda: ops.gemm(dy, w2, du, b_mn=True)),
                  ("dgrad-fc2 act2 (GELU' recomputed) + colsum", lambda: ops.gemm(dy, w2, du, b_mn=True, aux=u, act=2, colsum=cs)),
-                 ("dgrad-fc2 act4 (stored GELU') + colsum", lambda: ops.gemm(dy, w2, du, b_mn=True, aux=u, act=4, colsum=cs))):
+                 ("dgrad-fc2 act4 (stored GELU') + colsum", lambda: ops.gemm(dy, w2, du, b_mn=True, aux=u, act=4, colsum=cs)),
+                 ("dgrad-fc2 act4, narrow epilogue (no colsum)", lambda: ops.gemm(dy, w2, du, b_mn=True, aux=u, act=4))):
+    ms = t(fn)
+    print(f"{name:46s} {ms:7.3f} ms  {2.0 * M * D * HID / ms / 1e9:7.0f} TFLOP/s")
+
+# the fc1 weight gradient with / without the bias gradient summed from its dy tiles (colsum_a)
+dw = torch.zeros(HID, D, device="cuda")
+db = torch.zeros(HID, device="cuda")
+for name, fn in (("wgrad fc1 (split-K 7)", lambda: ops.gemm(du, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=7)),
+                 ("wgrad fc1 + colsum_a", lambda: ops.gemm(du, x, dw, a_mn=True, b_mn=True, accumulate=True, split_k=7, colsum_a=db))):
     ms = t(fn)
     print(f"{name:46s} {ms:7.3f} ms  {2.0 * M * D * HID / ms / 1e9:7.0f} TFLOP/s")
