@@ -86,17 +86,16 @@ __device__ __forceinline__ float gelu_q(float x, float& e) {
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float e;
-  const float xq = x * gelu_q(x, e);
-  return x >= 0.f ? x - xq : xq;
+  return fmaf(fabsf(x), 0.5f - gelu_q(x, e), 0.5f * x);   // = x Phi(x), no predicate
 }
 // GELU(x) and GELU'(x) = Phi(x) + x phi(x) from ONE evaluation of q (the fc1 epilogue stores the derivative for the
 // backward instead of the pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4)
 __device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) {
   float e;
-  const float q = gelu_q(x, e);
-  const float xq = x * q;
-  g = x >= 0.f ? x - xq : xq;
-  d = fmaf(x * 0.3989422804014327f, e, x >= 0.f ? 1.f - q : q);
+  const float r = 0.5f - gelu_q(x, e);                   // 0.5 - q = 0.5 erf(|x| / sqrt2) >= 0
+  // predicate-free sign handling: GELU = x Phi = 0.5 x + |x| r;  Phi = 0.5 + copysign(r, x)
+  g = fmaf(fabsf(x), r, 0.5f * x);
+  d = fmaf(x * 0.3989422804014327f, e, 0.5f + copysignf(r, x));
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
   float e;
