@@ -70,11 +70,12 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // GELU (exact-erf form) in the epilogue.  Phi(x) = 0.5 (1 + erf(x / sqrt2)) through Abramowitz-Stegun 7.1.26
 // (|err| <= 1.5e-7 on erf): with t = 1 / (1 + p |x| / sqrt2) and e = exp(-x^2 / 2),
-//     q = 0.5 (1 - erf(|x| / sqrt2)) = e * t * (a1' + t (a2' + t (a3' + t (a4' + t a5'))))      (a' = a / 2)
-//     Phi(x) = x >= 0 ? 1 - q : q
-// = 2 MUFU + 11 FMA-pipe instructions per element (erff is ~30): the fc1 epilogue is issue-bound -- it has to fit in
-// the 6144-cycle MMA time of a K = 768 tile -- so constants are folded wherever a multiply would only rescale.
-__device__ __forceinline__ float gelu_q(float x, float& e) {
+//     r = 0.5 erf(|x| / sqrt2) = 0.5 - e * t * (a1' + t (a2' + t (a3' + t (a4' + t a5'))))      (a' = a / 2)
+//     Phi(x) = 0.5 + copysign(r, x)       GELU = x Phi       GELU' = Phi + x phi,  phi = e / sqrt(2 pi)
+// = 2 MUFU + 9 FMA-pipe instructions for r and e, +2 for GELU, +2 more for GELU', no predicates (the sign goes through
+// one ALU-pipe LOP3): the fc1 epilogue is bound by the FMA pipe / issue -- it has to fit in the 6144-cycle MMA time of a
+// K = 768 tile -- so constants are folded wherever a multiply would only rescale.
+__device__ __forceinline__ float gelu_half_erf(float x, float& e) {
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.f)));
   e = exp2f(x * x * -0.72134752044448170f);            // exp(-x^2 / 2)
@@ -82,25 +83,24 @@ __device__ __forceinline__ float gelu_q(float x, float& e) {
   p = fmaf(p, t, 0.5f * 1.421413741f);
   p = fmaf(p, t, 0.5f * -0.284496736f);
   p = fmaf(p, t, 0.5f * 0.254829592f);
-  return p * t * e;
+  return fmaf(-(p * t), e, 0.5f);
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   float e;
-  return fmaf(fabsf(x), 0.5f - gelu_q(x, e), 0.5f * x);   // = x Phi(x), no predicate
+  return x * (0.5f + copysignf(gelu_half_erf(x, e), x));
 }
-// GELU(x) and GELU'(x) = Phi(x) + x phi(x) from ONE evaluation of q (the fc1 epilogue stores the derivative for the
-// backward instead of the pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4)
+// GELU(x) and GELU'(x) from ONE evaluation of r (the fc1 epilogue stores the derivative for the backward instead of the
+// pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4)
 __device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) {
   float e;
-  const float r = 0.5f - gelu_q(x, e);                   // 0.5 - q = 0.5 erf(|x| / sqrt2) >= 0
-  // predicate-free sign handling: GELU = x Phi = 0.5 x + |x| r;  Phi = 0.5 + copysign(r, x)
-  g = fmaf(fabsf(x), r, 0.5f * x);
-  d = fmaf(x * 0.3989422804014327f, e, 0.5f + copysignf(r, x));
+  const float phi_cdf = 0.5f + copysignf(gelu_half_erf(x, e), x);
+  g = x * phi_cdf;
+  d = fmaf(x * 0.3989422804014327f, e, phi_cdf);
 }
 __device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
   float e;
-  const float q = gelu_q(x, e);
-  return fmaf(x * 0.3989422804014327f, e, x >= 0.f ? 1.f - q : q);
+  const float phi_cdf = 0.5f + copysignf(gelu_half_erf(x, e), x);
+  return fmaf(x * 0.3989422804014327f, e, phi_cdf);
 }
 
 // Epilogue staging (warp-private, 32 rows x 128 B).  bf16: a row's 32 values = 4 x 16B chunks placed at slot
