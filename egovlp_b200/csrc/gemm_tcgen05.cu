@@ -69,65 +69,120 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 }
 
 // GELU (exact-erf form) in the epilogue.  Phi(x) = 0.5 (1 + erf(x / sqrt2)) through Abramowitz-Stegun 7.1.26
-// (|err| <= 1.5e-7 on erf): with t = 1 / (1 + p |x| / sqrt2) and e = exp(-x^2 / 2),
-//     r = 0.5 erf(|x| / sqrt2) = 0.5 - e * t * (a1' + t (a2' + t (a3' + t (a4' + t a5'))))      (a' = a / 2)
-//     Phi(x) = 0.5 + copysign(r, x)       GELU = x Phi       GELU' = Phi + x phi,  phi = e / sqrt(2 pi)
-// = 2 MUFU + 9 FMA-pipe instructions for r and e, +2 for GELU, +2 more for GELU', no predicates (the sign goes through
-// one ALU-pipe LOP3): the fc1 epilogue is bound by the FMA pipe / issue -- it has to fit in the 6144-cycle MMA time of a
-// K = 768 tile -- so constants are folded wherever a multiply would only rescale.
-__device__ __forceinline__ float gelu_half_erf(float x, float& e) {
+// (|err| <= 1.5e-7 on erf).  With u = k x, k = sqrt(log2(e) / 2) (so that exp(-x^2 / 2) = 2^(-u^2)),
+// t = 1 / (1 + p |x| / sqrt2) and e' = c exp(-x^2 / 2) = 2^(log2 c - u^2), c = 1 / (k sqrt(2 pi)):
+//     r = 0.5 erf(|x| / sqrt2) = 0.5 + e' t (b1 + t (b2 + t (b3 + t (b4 + t b5))))      (b = -a / (2 c))
+//     Phi(x) = 0.5 + copysign(r, x)       GELU = x Phi       GELU' = Phi + x phi = Phi + u e'
+// The fc1 epilogue has to fit in the 6144-cycle MMA time of a K = 768 tile with two warps per scheduler, i.e. ~24 issue
+// slots per element including the loads, packs and stores, so the arithmetic is packed two elements per instruction
+// (FFMA2 / FMUL2 / FADD2): per PAIR 4 MUFU + 2 FFMA (|u| needs the scalar form's abs modifier) + 2 LOP3 (copysign) +
+// 11 packed instructions, = 9.5 issue slots per element for GELU and GELU' together (17.4 in the scalar form).
+constexpr float GELU_K = 0.84932180028801907f;          // sqrt(log2(e) / 2)
+constexpr float GELU_PT = 0.27273749f;                  // 0.3275911 / sqrt2 / GELU_K
+constexpr float GELU_LOG2C = -1.0901312f;               // log2(c), c = 0.39894228 / GELU_K = 0.46971865
+constexpr float GELU_B1 = -0.5f * 0.254829592f / 0.46971865f, GELU_B2 = 0.5f * 0.284496736f / 0.46971865f,
+                GELU_B3 = -0.5f * 1.421413741f / 0.46971865f, GELU_B4 = 0.5f * 1.453152027f / 0.46971865f,
+                GELU_B5 = -0.5f * 1.061405429f / 0.46971865f;
+struct GeluConsts {       // packed constants, built once per warp (register pairs)
+  f32x2 k, nk, l2c, b1, b2, b3, b4, b5, half;
+  __device__ __forceinline__ GeluConsts()
+      : k(pk2(GELU_K, GELU_K)), nk(pk2(-GELU_K, -GELU_K)), l2c(pk2(GELU_LOG2C, GELU_LOG2C)), b1(pk2(GELU_B1, GELU_B1)),
+        b2(pk2(GELU_B2, GELU_B2)), b3(pk2(GELU_B3, GELU_B3)), b4(pk2(GELU_B4, GELU_B4)), b5(pk2(GELU_B5, GELU_B5)),
+        half(pk2(0.5f, 0.5f)) {}
+};
+// two elements: Phi (returned), u = k x and e' for the derivative
+__device__ __forceinline__ f32x2 gelu_phi2(const GeluConsts& gc, float x0, float x1, f32x2 x, f32x2& u, f32x2& e) {
+  u = mul2(x, gc.k);
+  float u0, u1, a0, a1, t0, t1, e0, e1, r0, r1;
+  up2(u, u0, u1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(fabsf(u0), GELU_PT, 1.f)));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(fabsf(u1), GELU_PT, 1.f)));
+  up2(fma2(mul2(x, gc.nk), u, gc.l2c), a0, a1);          // log2 c - u^2
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const f32x2 t = pk2(t0, t1);
+  e = pk2(e0, e1);
+  f32x2 p = fma2(t, gc.b5, gc.b4);
+  p = fma2(p, t, gc.b3);
+  p = fma2(p, t, gc.b2);
+  p = fma2(p, t, gc.b1);
+  up2(fma2(mul2(p, t), e, gc.half), r0, r1);
+  return add2(pk2(copysignf(r0, x0), copysignf(r1, x1)), gc.half);
+}
+__device__ __forceinline__ void gelu2(const GeluConsts& gc, float& x0, float& x1) {            // in place
+  const f32x2 x = pk2(x0, x1);
+  f32x2 u, e;
+  up2(mul2(x, gelu_phi2(gc, x0, x1, x, u, e)), x0, x1);
+}
+// GELU(x) and GELU'(x) from ONE evaluation of Phi (the fc1 epilogue stores the derivative for the backward instead of
+// the pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4); both returned packed as bf16x2
+__device__ __forceinline__ void gelu_and_grad2(const GeluConsts& gc, float x0, float x1, uint32_t& g_bf, uint32_t& d_bf) {
+  const f32x2 x = pk2(x0, x1);
+  f32x2 u, e;
+  const f32x2 phi = gelu_phi2(gc, x0, x1, x, u, e);
+  float g0, g1, d0, d1;
+  up2(mul2(x, phi), g0, g1);
+  up2(fma2(u, e, phi), d0, d1);
+  g_bf = pack_bf16x2(g0, g1);
+  d_bf = pack_bf16x2(d0, d1);
+}
+// scalar form of the derivative for the legacy act = 2 epilogue (recompute GELU' from the stored pre-activation)
+__device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
   float t;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.f)));
-  e = exp2f(x * x * -0.72134752044448170f);            // exp(-x^2 / 2)
+  const float e = exp2f(x * x * -0.72134752044448170f);            // exp(-x^2 / 2)
   float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   p = fmaf(p, t, 0.5f * 1.421413741f);
   p = fmaf(p, t, 0.5f * -0.284496736f);
   p = fmaf(p, t, 0.5f * 0.254829592f);
-  return fmaf(-(p * t), e, 0.5f);
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  float e;
-  return x * (0.5f + copysignf(gelu_half_erf(x, e), x));
-}
-// GELU(x) and GELU'(x) from ONE evaluation of r (the fc1 epilogue stores the derivative for the backward instead of the
-// pre-activation: the dgrad-fc2 epilogue then only multiplies, act = 4)
-__device__ __forceinline__ void gelu_and_grad_fast(float x, float& g, float& d) {
-  float e;
-  const float phi_cdf = 0.5f + copysignf(gelu_half_erf(x, e), x);
-  g = x * phi_cdf;
-  d = fmaf(x * 0.3989422804014327f, e, phi_cdf);
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {     // Phi(x) + x phi(x)
-  float e;
-  const float phi_cdf = 0.5f + copysignf(gelu_half_erf(x, e), x);
+  const float phi_cdf = 0.5f + copysignf(fmaf(-(p * t), e, 0.5f), x);
   return fmaf(x * 0.3989422804014327f, e, phi_cdf);
 }
 
 // Epilogue staging (warp-private, 32 rows x 128 B).  bf16: a row's 32 values = 4 x 16B chunks placed at slot
-// (c ^ ((r>>1)&3)) + 4*(r&1) so that both the row-owner writes and the 4-lanes-per-row reads are conflict-free.
-__device__ __forceinline__ void stage_bf16_rows(uint32_t stg, int lane, const float (&v)[32]) {
+// (c ^ ((r>>1)&3)) + 4*((r&1)^which) so that both the row-owner writes and the 4-lanes-per-row reads are conflict-free;
+// `which` = 0 / 1 picks one of two disjoint halves of the buffer, so two bf16 outputs (GELU and GELU') can be staged
+// together and leave after ONE warp barrier.
+__device__ __forceinline__ void stage_bf16_rows_packed(uint32_t stg, int lane, const uint32_t (&w)[16], int which) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const uint32_t a = stg + lane * 128 + ((((c ^ ((lane >> 1) & 3)) + 4 * (lane & 1))) << 4);
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(v[8 * c], v[8 * c + 1])),
-                 "r"(pack_bf16x2(v[8 * c + 2], v[8 * c + 3])), "r"(pack_bf16x2(v[8 * c + 4], v[8 * c + 5])),
-                 "r"(pack_bf16x2(v[8 * c + 6], v[8 * c + 7])));
+    const uint32_t a = stg + lane * 128 + ((((c ^ ((lane >> 1) & 3)) + 4 * ((lane & 1) ^ which))) << 4);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(w[4 * c]), "r"(w[4 * c + 1]), "r"(w[4 * c + 2]),
+                 "r"(w[4 * c + 3]));
   }
 }
+__device__ __forceinline__ void stage_bf16_rows(uint32_t stg, int lane, const float (&v)[32], int which) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  stage_bf16_rows_packed(stg, lane, w, which);
+}
 __device__ __forceinline__ void store_bf16_coalesced(const uint8_t* stg_gen, int lane, bf16* out, long long ldo, int row0,
-                                                     int n0, int M) {
+                                                     int n0, int M, int which) {
   const int c = lane & 3;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rl = 8 * i + (lane >> 2), grow = row0 + rl;
     if (grow < M) {
-      const uint4 x = *reinterpret_cast<const uint4*>(stg_gen + rl * 128 + (((c ^ ((rl >> 1) & 3)) + 4 * (rl & 1)) << 4));
+      const uint4 x =
+          *reinterpret_cast<const uint4*>(stg_gen + rl * 128 + (((c ^ ((rl >> 1) & 3)) + 4 * ((rl & 1) ^ which)) << 4));
       *reinterpret_cast<uint4*>(out + (long long)grow * ldo + n0 + c * 8) = x;
     }
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO>
+// MODE specialises the epilogue at compile time for the step's four hot forms (the generic epilogue decides everything
+// per chunk from runtime fields: ~100 branches and ~120 integer instructions per 32-column chunk, which made the fc1,
+// fc2-dgrad and residual GEMMs epilogue-bound and spilled the kernel out of the instruction cache):
+enum EpiMode {
+  EPI_GENERIC = 0,   // everything EpiParams can express
+  EPI_BF16 = 1,      // alpha, bias, optional column scale -> bf16                      (qkv, plain dgrad)
+  EPI_ACT3 = 2,      // bias -> GELU -> bf16, GELU' -> bf16 out2                         (Mlp.fc1 forward)
+  EPI_MUL_AUX = 3,   // x bf16 aux -> bf16                                               (Mlp.fc2 input gradient)
+  EPI_RES_F32 = 4,   // bias + fp32 residual -> fp32                                     (proj / fc2 forward)
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                          int K, int num_m_blocks, int num_n_blocks, int kb_per_split, int num_splits, EpiParams ep) {
@@ -183,6 +238,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // Register split (setmaxnreg): the control warpgroup (TMA, MMA issue, TMEM allocation, wgrad column sums) gives
+  // registers back, the two epilogue warpgroups take them for their one-chunk-ahead operand prefetch:
+  // 128 x 64 + 256 x 216 <= the CTA's launch allocation of 384 x 168.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -315,33 +375,123 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ===================== epilogue: TMEM -> registers -> HBM =====================
+    // Software-pipelined per 32-column chunk: the TMEM load of chunk c+1 is issued as soon as chunk c has been copied
+    // out of its registers, and the per-element global operands of chunk c+1 (fp32 residual, bf16 aux) are requested the
+    // moment chunk c has consumed its own -- across tile boundaries too -- so neither latency is paid per chunk (with
+    // two epilogue warps per scheduler there is nobody else to hide it).
     const int e = warp - 4;
     const int q = warp & 3;       // TMEM lane quarter this warp may read
     const int half = e >> 2;      // which half of the BLOCK_N columns
     constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    constexpr int NCH = COLS_PER_WARP / 32;
     const uint32_t stg = epi_stage + e * 4096;
     const uint8_t* stg_gen = smem_gen + (stg - smem_base);
+    const GeluConsts gc;
+    // epilogue fields: compile-time constants in the specialised modes
+    constexpr bool GEN = MODE == EPI_GENERIC;
+    const int e_act = GEN ? ep.act : (MODE == EPI_ACT3 ? 3 : MODE == EPI_MUL_AUX ? 4 : 0);
+    const int e_out_mode = GEN ? ep.out_mode : (MODE == EPI_RES_F32 ? 1 : 0);
+    const float* e_residual = (GEN || MODE == EPI_RES_F32) ? ep.residual : nullptr;
+    const bf16* e_aux = (GEN || MODE == EPI_MUL_AUX) ? ep.aux : nullptr;
+    float* e_colsum = GEN ? ep.colsum : nullptr;
+    bf16* e_out2 = (GEN || MODE == EPI_ACT3) ? ep.out2 : nullptr;
+    const int e_col_scale_ncols = (GEN || MODE == EPI_BF16) ? ep.col_scale_ncols : 0;
+    const int e_res_row_mod = GEN ? ep.res_row_mod : 0;
+    // act 4 with a plain bf16 output: multiply in the row-per-lane register domain (4 x 16-byte loads of the lane's own
+    // aux row) and leave through the cheap staged bf16 store -- the "wide" float4 path costs ~3.5x the instructions per
+    // element and made the fc2 input-gradient GEMM epilogue-bound
+    const bool narrow4 = e_act == 4 && e_out_mode == 0 && e_residual == nullptr && e_colsum == nullptr;
+    const bool wide = !narrow4 && (e_out_mode != 0 || e_residual != nullptr || e_act == 2 || e_act == 4 ||
+                                   e_colsum != nullptr);
+    const bool wide_aux = wide && (e_act == 2 || e_act == 4);
+    const int c4 = lane & 7, wr = lane >> 3;         // wide path: lane -> (row within a group of 4, float4 column)
+    float4 pres[8];        // prefetched residual (wide path)
+    uint32_t paux[16];     // prefetched aux: 8 x uint2 (wide path) or 4 x uint4 of the lane's own row (narrow4)
+    int pre_tag = -1;      // (unit, chunk) whose operands the prefetch registers hold
+    auto prefetch = [&](int prow0, int pn0) {
+      if (narrow4) {
+        const int grow = min(prow0 + lane, M - 1);
+        const uint4* ap = reinterpret_cast<const uint4*>(e_aux + (long long)grow * ep.ldaux + pn0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 t = __ldg(ap + i);
+          paux[4 * i] = t.x; paux[4 * i + 1] = t.y; paux[4 * i + 2] = t.z; paux[4 * i + 3] = t.w;
+        }
+      } else if (wide) {
+        const int col = pn0 + c4 * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int grow = min(prow0 + 4 * i + wr, M - 1);          // rows clamped, no branches
+          if (e_residual) {
+            const int rrow = e_res_row_mod ? grow % e_res_row_mod : grow;
+            pres[i] = __ldg(reinterpret_cast<const float4*>(e_residual + (long long)rrow * ep.ldr + col));
+          }
+          if (wide_aux) {
+            const uint2 t = __ldg(reinterpret_cast<const uint2*>(e_aux + (long long)grow * ep.ldaux + col));
+            paux[2 * i] = t.x; paux[2 * i + 1] = t.y;
+          }
+        }
+      }
+    };
+    auto tile_row0 = [&](int unit) {
+      const int tile = unit % num_tiles;
+      return (tile / num_n_blocks) * C::TILE_M + (int)rank * BLOCK_M + q * 32;
+    };
+    auto tile_n0 = [&](int unit) {
+      const int tile = unit % num_tiles;
+      return (tile % num_n_blocks) * BLOCK_N + half * COLS_PER_WARP;
+    };
+    const bool has_pre = narrow4 || (wide && (e_residual != nullptr || wide_aux));
+    if (has_pre && worker < num_units && tile_n0(worker) < N) {
+      prefetch(tile_row0(worker), tile_n0(worker));
+      pre_tag = worker * NCH;
+    }
     int it = 0;
     for (int unit = worker; unit < num_units; unit += num_workers, ++it) {
-      const int split = unit / num_tiles, tile = unit - split * num_tiles;
-      const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int row0 = tile_row0(unit);     // first of this warp's 32 rows
+      const int nt0 = tile_n0(unit);
+      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
+      uint32_t r[32];
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const int row0 = m_blk * C::TILE_M + (int)rank * BLOCK_M + q * 32;     // first of this warp's 32 rows
-      const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
+      tmem_ld_32x32b_x32(t_row, r);
       // Each chunk: TMEM -> registers in row-owner layout (lane = row, 32 consecutive columns) -> per-column math
       // -> warp-private swizzled smem transpose -> coalesced layout (a row's 64/128 B handled by 4/8 adjacent lanes)
       // -> per-element operands (residual, aux) and full-sector global stores.
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
+      for (int c = 0; c < NCH; ++c) {
+        const int n0 = nt0 + 32 * c;
+        const bool valid = n0 < N;     // warp-uniform
+        float4 bq[8];
+        if (valid && ep.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bq[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
-        if (c + 32 == COLS_PER_WARP) {
+        float v[32];
+        {
+          const f32x2 al = pk2(ep.alpha, ep.alpha);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            up2(fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), al, pk2(bq[j].x, bq[j].y)), v[4 * j],
+                v[4 * j + 1]);
+            up2(fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), al, pk2(bq[j].z, bq[j].w)),
+                v[4 * j + 2], v[4 * j + 3]);
+          }
+        }
+        if (c + 1 < NCH) {
+          tmem_ld_32x32b_x32(t_row + 32 * (c + 1), r);       // next chunk, in flight during this chunk's math
+        } else {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -350,73 +500,53 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             else mbar_arrive(tempty_bar + 8 * acc);
           }
         }
-        const int n0 = n_blk * BLOCK_N + half * COLS_PER_WARP + c;
-        if (n0 >= N) continue;     // warp-uniform
-        float v[32];
-        {
-          const f32x2 al = pk2(ep.alpha, ep.alpha);
-          const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+        if (!valid) continue;
+        // operands of this chunk (already in flight unless this is a cold start), and where the next ones come from
+        if (has_pre && pre_tag != unit * NCH + c) prefetch(row0, n0);
+        int nunit = unit, nc = c + 1;
+        if (nc == NCH) { nunit = unit + num_workers; nc = 0; }
+        const bool nvalid = has_pre && nunit < num_units && tile_n0(nunit) + 32 * nc < N;
+        const int nrow0 = nvalid ? tile_row0(nunit) : 0, nn0 = nvalid ? tile_n0(nunit) + 32 * nc : 0;
+
+        if (n0 < e_col_scale_ncols) {
+          const f32x2 sc = pk2(ep.col_scale, ep.col_scale);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = ep.bias ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            up2(fma2(pk2(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])), al, pk2(b.x, b.y)), v[4 * j], v[4 * j + 1]);
-            up2(fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), al, pk2(b.z, b.w)), v[4 * j + 2],
-                v[4 * j + 3]);
-          }
+          for (int j = 0; j < 16; ++j) up2(mul2(pk2(v[2 * j], v[2 * j + 1]), sc), v[2 * j], v[2 * j + 1]);
         }
-        if (n0 < ep.col_scale_ncols) {
+        if (e_act == 3) {                     // out = GELU(v), out2 = GELU'(v): both staged side by side, one round trip
+          uint32_t og[16], od[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= ep.col_scale;
-        }
-        if (ep.act == 3) {                     // out = GELU(v), out2 = GELU'(v)
-          float d[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) gelu_and_grad_fast(v[j], v[j], d[j]);
-          if (ep.out2) {
-            stage_bf16_rows(stg, lane, d);
-            __syncwarp();
-            store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
-            __syncwarp();
-          }
-        } else {
-          if (ep.out2) {
-            stage_bf16_rows(stg, lane, v);
-            __syncwarp();
-            store_bf16_coalesced(stg_gen, lane, ep.out2, ep.ldo2, row0, n0, M);
-            __syncwarp();
-          }
-          if (ep.act == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
-          }
-        }
-        // act 4 with a plain bf16 output: multiply in the row-per-lane register domain (4 x 16-byte loads of the lane's
-        // own aux row) and leave through the cheap staged bf16 store -- the "wide" float4 path below costs ~3.5x the
-        // instructions per element and made the fc2 input-gradient GEMM epilogue-bound (1.79 ms vs 0.82 ms plain)
-        const bool narrow4 = ep.act == 4 && ep.out_mode == 0 && ep.residual == nullptr && ep.colsum == nullptr;
-        if (narrow4) {
-          const int grow = min(row0 + lane, M - 1);
-          const uint4* ap = reinterpret_cast<const uint4*>(ep.aux + (long long)grow * ep.ldaux + n0);
-          uint4 a4[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a4[c] = __ldg(ap + c);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t w[4] = {a4[c].x, a4[c].y, a4[c].z, a4[c].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = unpack_bf16x2(w[i]);
-              v[8 * c + 2 * i] *= f.x;
-              v[8 * c + 2 * i + 1] *= f.y;
-            }
-          }
-        }
-        const bool wide = !narrow4 && (ep.out_mode != 0 || ep.residual != nullptr || ep.act == 2 || ep.act == 4 ||
-                                       ep.colsum != nullptr);
-        if (!wide) {
-          stage_bf16_rows(stg, lane, v);
+          for (int j = 0; j < 16; ++j) gelu_and_grad2(gc, v[2 * j], v[2 * j + 1], og[j], od[j]);
+          stage_bf16_rows_packed(stg, lane, og, 0);
+          if (e_out2) stage_bf16_rows_packed(stg, lane, od, 1);
           __syncwarp();
-          store_bf16_coalesced(stg_gen, lane, reinterpret_cast<bf16*>(ep.out), ep.ldo, row0, n0, M);
+          store_bf16_coalesced(stg_gen, lane, reinterpret_cast<bf16*>(ep.out), ep.ldo, row0, n0, M, 0);
+          if (e_out2) store_bf16_coalesced(stg_gen, lane, e_out2, ep.ldo2, row0, n0, M, 1);
+          __syncwarp();   // staging buffer is reused by the next chunk
+          continue;
+        }
+        if (e_out2) {      // pre-activation (act 1) or a second copy
+          stage_bf16_rows(stg, lane, v, 1);
+          __syncwarp();
+          store_bf16_coalesced(stg_gen, lane, e_out2, ep.ldo2, row0, n0, M, 1);
+          if (wide) __syncwarp();        // the fp32 staging below overwrites the whole buffer
+        }
+        if (e_act == 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) gelu2(gc, v[2 * j], v[2 * j + 1]);
+        }
+        if (narrow4) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 f = unpack_bf16x2(paux[j]);
+            up2(mul2(pk2(v[2 * j], v[2 * j + 1]), pk2(f.x, f.y)), v[2 * j], v[2 * j + 1]);
+          }
+          if (nvalid) { prefetch(nrow0, nn0); pre_tag = nunit * NCH + nc; }
+        }
+        if (!wide) {
+          stage_bf16_rows(stg, lane, v, 0);
+          __syncwarp();
+          store_bf16_coalesced(stg_gen, lane, reinterpret_cast<bf16*>(ep.out), ep.ldo, row0, n0, M, 0);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -425,53 +555,46 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                          "f"(v[4 * j + 2]), "f"(v[4 * j + 3]));
           }
           __syncwarp();
-          const int c4 = lane & 7;
           const int col = n0 + c4 * 4;
-          // issue every per-element global load of the chunk first (rows clamped, no branches) so that 8 independent
-          // requests per lane are in flight instead of one latency-bound load per iteration
-          float4 resv[8];
-          uint2 auxv[8];
+          float4 x[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int grow = min(row0 + 4 * i + (lane >> 3), M - 1);
-            if (ep.residual) {
-              const int rrow = ep.res_row_mod ? grow % ep.res_row_mod : grow;
-              resv[i] = __ldg(reinterpret_cast<const float4*>(ep.residual + (long long)rrow * ep.ldr + col));
+            const int rl = 4 * i + wr;
+            x[i] = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+            if (e_act == 2) {
+              const float2 p0 = unpack_bf16x2(paux[2 * i]), p1 = unpack_bf16x2(paux[2 * i + 1]);
+              x[i].x *= gelu_grad_fast(p0.x); x[i].y *= gelu_grad_fast(p0.y);
+              x[i].z *= gelu_grad_fast(p1.x); x[i].w *= gelu_grad_fast(p1.y);
+            } else if (e_act == 4) {          // aux already holds GELU'(pre-activation)
+              const float2 p0 = unpack_bf16x2(paux[2 * i]), p1 = unpack_bf16x2(paux[2 * i + 1]);
+              x[i].x *= p0.x; x[i].y *= p0.y; x[i].z *= p1.x; x[i].w *= p1.y;
             }
-            if (ep.act == 2 || ep.act == 4) auxv[i] = __ldg(reinterpret_cast<const uint2*>(ep.aux + (long long)grow * ep.ldaux + col));
+            if (e_residual) { x[i].x += pres[i].x; x[i].y += pres[i].y; x[i].z += pres[i].z; x[i].w += pres[i].w; }
           }
+          // this chunk's operands are consumed: request the next chunk's before the stores go out
+          if (nvalid) { prefetch(nrow0, nn0); pre_tag = nunit * NCH + nc; }
           float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int rl = 4 * i + (lane >> 3), grow = row0 + rl;
-            float4 x = *reinterpret_cast<const float4*>(stg_gen + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-            if (ep.act == 2) {
-              const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
-              x.x *= gelu_grad_fast(p0.x); x.y *= gelu_grad_fast(p0.y);
-              x.z *= gelu_grad_fast(p1.x); x.w *= gelu_grad_fast(p1.y);
-            } else if (ep.act == 4) {          // aux already holds GELU'(pre-activation)
-              const float2 p0 = unpack_bf16x2(auxv[i].x), p1 = unpack_bf16x2(auxv[i].y);
-              x.x *= p0.x; x.y *= p0.y; x.z *= p1.x; x.w *= p1.y;
-            }
-            if (ep.residual) { x.x += resv[i].x; x.y += resv[i].y; x.z += resv[i].z; x.w += resv[i].w; }
+            const int grow = row0 + 4 * i + wr;
             if (grow < M) {
-              cs.x += x.x; cs.y += x.y; cs.z += x.z; cs.w += x.w;
-              if (ep.out_mode == 0) {
+              cs.x += x[i].x; cs.y += x[i].y; cs.z += x[i].z; cs.w += x[i].w;
+              if (e_out_mode == 0) {
                 *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(ep.out) + (long long)grow * ep.ldo + col) =
-                    make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
-              } else if (ep.out_mode == 1) {
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col) = x;
+                    make_uint2(pack_bf16x2(x[i].x, x[i].y), pack_bf16x2(x[i].z, x[i].w));
+              } else if (e_out_mode == 1) {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col) = x[i];
               } else {
-                red_add_v4(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col, x.x, x.y, x.z, x.w);
+                red_add_v4(reinterpret_cast<float*>(ep.out) + (long long)grow * ep.ldo + col, x[i].x, x[i].y, x[i].z, x[i].w);
               }
             }
           }
-          if (ep.colsum) {     // lanes l, l+8, l+16, l+24 hold the same 4 columns: fold, then one vector atomic per column group
+          if (e_colsum) {     // lanes l, l+8, l+16, l+24 hold the same 4 columns: fold, then one vector atomic per column group
             cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 8); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 8);
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 8); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 8);
             cs.x += __shfl_xor_sync(0xffffffffu, cs.x, 16); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, 16);
             cs.z += __shfl_xor_sync(0xffffffffu, cs.z, 16); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, 16);
-            if (lane < 8) red_add_v4(ep.colsum + col, cs.x, cs.y, cs.z, cs.w);
+            if (lane < 8) red_add_v4(e_colsum + col, cs.x, cs.y, cs.z, cs.w);
           }
         }
         __syncwarp();   // staging buffer is reused by the next chunk
@@ -489,7 +612,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO, int MODE = EPI_GENERIC>
 int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int splits,
            const EpiParams& ep, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, TWO>;
@@ -507,7 +630,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   const int kb_per_split = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per_split - 1) / kb_per_split;  // no empty splits
   const int units = num_m_blocks * num_n_blocks * splits;
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN, TWO>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, A_MN, B_MN, TWO, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     EGOVLP_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -539,6 +662,20 @@ int dispatch_major(int a_mn, int b_mn, const void* A, long long lda, const void*
   if (!a_mn && b_mn) return launch<BLOCK_N, false, true, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
   if (a_mn && b_mn) return launch<BLOCK_N, true, true, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
   return launch<BLOCK_N, true, false, TWO>(A, lda, B, ldb, M, N, K, splits, ep, stream);
+}
+
+// Which specialised epilogue (if any) computes exactly what `ep` asks for; EGOVLP_GEMM_GENERIC_EPI=1 keeps every call on
+// the generic one (the kernel tests run both and compare).
+inline int epi_mode(const EpiParams& ep) {
+  const char* g = getenv("EGOVLP_GEMM_GENERIC_EPI");
+  if (g && g[0] == '1') return EPI_GENERIC;
+  if (ep.colsum || ep.res_row_mod) return EPI_GENERIC;
+  const bool no_scale = ep.col_scale_ncols == 0;
+  if (ep.act == 0 && ep.out_mode == 0 && !ep.residual && !ep.out2) return EPI_BF16;
+  if (ep.act == 3 && ep.out_mode == 0 && !ep.residual && ep.out2 && no_scale) return EPI_ACT3;
+  if (ep.act == 4 && ep.out_mode == 0 && !ep.residual && !ep.out2 && no_scale) return EPI_MUL_AUX;
+  if (ep.act == 0 && ep.out_mode == 1 && ep.residual && !ep.out2 && no_scale) return EPI_RES_F32;
+  return EPI_GENERIC;
 }
 
 // EGOVLP_GEMM_1CTA=1 keeps every shape on the single-CTA kernels (tests exercise both)
@@ -584,8 +721,20 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   // CTA-pair 256 x 256 tiles for the K-major-A shapes (fwd, dgrad); the token-contraction wgrad (both operands
   // MN-major, split-K) measured 3-8 % faster on single-CTA 128 x 256 tiles (tools/bench_gemm_modes.py)
-  if (N % 256 == 0 && !force_one_cta() && !(a_mn_major && b_mn_major))
+  if (N % 256 == 0 && !force_one_cta() && !(a_mn_major && b_mn_major)) {
+    if (!a_mn_major) {       // the step's hot forms get a compile-time specialised epilogue
+      const int mode = epi_mode(ep);
+#define EGOVLP_GEMM_MODE(MODE)                                                                               \
+  return b_mn_major ? launch<256, false, true, true, MODE>(A, lda, B, ldb, M, N, K, split_k, ep, st)          \
+                    : launch<256, false, false, true, MODE>(A, lda, B, ldb, M, N, K, split_k, ep, st)
+      if (mode == EPI_BF16) { EGOVLP_GEMM_MODE(EPI_BF16); }
+      if (mode == EPI_ACT3) { EGOVLP_GEMM_MODE(EPI_ACT3); }
+      if (mode == EPI_MUL_AUX) { EGOVLP_GEMM_MODE(EPI_MUL_AUX); }
+      if (mode == EPI_RES_F32) { EGOVLP_GEMM_MODE(EPI_RES_F32); }
+#undef EGOVLP_GEMM_MODE
+    }
     return dispatch_major<256, true>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
+  }
   if (N % 256 == 0) return dispatch_major<256, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
   return dispatch_major<128, false>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);
 }

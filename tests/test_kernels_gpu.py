@@ -118,6 +118,44 @@ def test_gemm_epilogues(ops, gemm_mode):
     assert rel_err(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(1570, 768, 256), (515, 3072, 768), (4099, 1024, 128)])
+def test_gemm_specialised_epilogues_match_the_generic_one(ops, monkeypatch, M, N, K):
+    """The CTA-pair kernels carry compile-time specialised epilogues for the step's hot forms (bias -> bf16, GELU + GELU',
+    x aux, bias + fp32 residual -> fp32); EGOVLP_GEMM_GENERIC_EPI=1 routes the same calls through the generic epilogue.
+    Same arithmetic in the same order: the results must be bit-identical (ragged last m-block, several tiles per CTA)."""
+    a, b = mk((M, K), 30), mk((N, K), 31, 0.06)
+    wt = mk((K, N), 32, 0.06)                      # MN-major B (dgrad form)
+    bias = mk((N,), 33, dtype=torch.float32)
+    res = mk((M, N), 34, dtype=torch.float32)
+    aux = mk((M, N), 35)
+
+    def run():
+        outs = []
+        o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, o, bias=bias, col_scale=0.125, col_scale_ncols=256); outs.append(o)            # EPI_BF16
+        o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, wt, o, b_mn=True); outs.append(o)                                                  # EPI_BF16, dgrad
+        h, d = torch.empty_like(o), torch.empty_like(o)
+        ops.gemm(a, b, h, bias=bias, act=3, out2=d); outs += [h, d]                                     # EPI_ACT3
+        o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, wt, o, b_mn=True, aux=aux, act=4); outs.append(o)                                   # EPI_MUL_AUX
+        o = torch.empty(M, N, device="cuda", dtype=torch.float32)
+        ops.gemm(a, b, o, bias=bias, residual=res); outs.append(o)                                      # EPI_RES_F32
+        torch.cuda.synchronize()
+        return outs
+
+    monkeypatch.setenv("EGOVLP_GEMM_GENERIC_EPI", "1")
+    ref = run()
+    monkeypatch.setenv("EGOVLP_GEMM_GENERIC_EPI", "0")
+    got = run()
+    for i, (r, g) in enumerate(zip(ref, got)):
+        assert torch.equal(r, g), i
+    acc = a.float() @ b.float().t() + bias
+    assert rel_err(got[5], acc + res) < 2e-5
+    assert rel_err(got[2], torch.nn.functional.gelu(acc)) < 4e-3
+    assert rel_err(got[4], (a.float() @ wt.float()) * aux.float()) < 4e-3
+
+
 def test_gemm_strided_views(ops, gemm_mode):
     """Operands / outputs that are column slices of wider buffers (ld > width)."""
     M, N, K = 384, 256, 192

@@ -38,6 +38,16 @@ for name, fn in (("fc1 plain", lambda: ops.gemm(x, w1, h, bias=b1)),
     ms = t(fn)
     print(f"{name:46s} {ms:7.3f} ms  {2.0 * M * D * HID / ms / 1e9:7.0f} TFLOP/s")
 
+# the memory-bound residual GEMMs (proj / fc2: fp32 residual stream in, fp32 out) and the QKV projection
+xr, wp, bp = torch.randn(M, D, device="cuda"), rnd(D, D), rnd(D, dt=torch.float32)
+yr = torch.empty_like(xr)
+wq, q3 = rnd(3 * D, D), torch.empty(M, 3 * D, device="cuda", dtype=torch.bfloat16)
+for name, fn, fl, gb in (("proj + fp32 residual -> fp32", lambda: ops.gemm(x, wp, yr, bias=bp, residual=xr), 2.0 * M * D * D, M * D * 10e-9),
+                         ("fc2 + fp32 residual -> fp32", lambda: ops.gemm(h, w2, yr, bias=bp, residual=xr), 2.0 * M * D * HID, M * (D * 8 + HID * 2) * 1e-9),
+                         ("qkv (q columns scaled)", lambda: ops.gemm(x, wq, q3, bias=None, col_scale=0.125, col_scale_ncols=D), 2.0 * M * D * 3 * D, M * D * 8e-9)):
+    ms = t(fn)
+    print(f"{name:46s} {ms:7.3f} ms  {fl / ms / 1e9:7.0f} TFLOP/s  {gb / ms * 1e3:6.0f} GB/s")
+
 # the fc1 weight gradient with / without the bias gradient summed from its dy tiles (colsum_a)
 dw = torch.zeros(HID, D, device="cuda")
 db = torch.zeros(HID, device="cuda")
