@@ -26,8 +26,14 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+#ifndef EGOVLP_EPI16
+#define EGOVLP_EPI16 0
+#endif
+// Epilogue warps: 8 (two per scheduler).  -DEGOVLP_EPI16=1 builds the specialised CTA-pair kernels with 16 (four per
+// scheduler, 32 rows x 64 columns each, 5 smem stages, no look-ahead): measured 3-10 % SLOWER on every hot form
+// (fc1 1.075 vs 1.040 ms, fc2-dgrad 1.052 vs 0.941, proj 0.379 vs 0.337) -- the step runs at the board's power cap
+// (SM clock 1.6-1.7 of 1.965 GHz), where time follows the energy of the instructions and bytes, not their latency.
+__host__ __device__ constexpr int epi_warps(bool two, int mode) { return (two && mode != 0 && EGOVLP_EPI16) ? 16 : 8; }
 constexpr int MN_ATOM_BYTES = BLOCK_K * 128;  // one 64(mn) x BLOCK_K(k) MN-major slab
 
 struct EpiParams {
@@ -52,14 +58,15 @@ struct EpiParams {
 // TWO = CTA pair (cta_group::2): a 256 x 256 tile per cluster, each CTA stages its 128 rows of A and HALF of B
 // (128 of the 256 n-rows).  Every smem byte then feeds twice the MMA work, which is what the 128 B/clk shared
 // memory port needs: in single-CTA mode TMA writes (96 B/clk) + UMMA operand reads (96 B/clk) oversubscribe it.
-template <int BLOCK_N, bool TWO>
+template <int BLOCK_N, bool TWO, int EW = 8>
 struct Cfg {
   static constexpr int B_ROWS = TWO ? BLOCK_N / 2 : BLOCK_N;
   static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256 && !TWO) ? 4 : 6;
+  static constexpr int STAGES = (BLOCK_N == 256 && !TWO) ? 4 : (EW == 16 ? 5 : 6);   // 16 x 4 KB of staging costs a stage
+  static constexpr int NUM_THREADS = (4 + EW) * 32;
   static constexpr int TILE_M = TWO ? 2 * BLOCK_M : BLOCK_M;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 4096;
+  static constexpr int EPI_STAGE_BYTES = EW * 4096;
   static constexpr int SMEM_BYTES =
       STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -183,10 +190,11 @@ enum EpiMode {
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO, int MODE>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((4 + epi_warps(TWO, MODE)) * 32, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N,
                          int K, int num_m_blocks, int num_n_blocks, int kb_per_split, int num_splits, EpiParams ep) {
-  using C = Cfg<BLOCK_N, TWO>;
+  constexpr int EW = epi_warps(TWO, MODE);
+  using C = Cfg<BLOCK_N, TWO, EW>;
   const uint32_t rank = TWO ? cluster_ctarank() : 0u;       // CTA of the pair; rank 0 issues the MMAs
   const int worker = TWO ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int num_workers = TWO ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -224,7 +232,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + 8 * a, 1);
-      mbar_init(tempty_bar + 8 * a, NUM_EPI_WARPS * (TWO ? 2 : 1));   // pair: both CTAs' epilogues report to rank 0
+      mbar_init(tempty_bar + 8 * a, EW * (TWO ? 2 : 1));   // pair: both CTAs' epilogues report to rank 0
     }
     fence_mbar_init();
   }
@@ -240,9 +248,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   // Register split (setmaxnreg): the control warpgroup (TMA, MMA issue, TMEM allocation, wgrad column sums) gives
   // registers back, the two epilogue warpgroups take them for their one-chunk-ahead operand prefetch:
-  // 128 x 64 + 256 x 216 <= the CTA's launch allocation of 384 x 168.
+  // 128 x 64 + 256 x 216 <= the CTA's launch allocation of 384 x 168 (16 epilogue warps: 128 x 56 + 512 x 104 <= 640 x 96).
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+  if (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -377,7 +386,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    if (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
     // ===================== epilogue: TMEM -> registers -> HBM =====================
     // Software-pipelined per 32-column chunk: the TMEM load of chunk c+1 is issued as soon as chunk c has been copied
     // out of its registers, and the per-element global operands of chunk c+1 (fp32 residual, bf16 aux) are requested the
@@ -385,8 +395,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // two epilogue warps per scheduler there is nobody else to hide it).
     const int e = warp - 4;
     const int q = warp & 3;       // TMEM lane quarter this warp may read
-    const int half = e >> 2;      // which half of the BLOCK_N columns
-    constexpr int COLS_PER_WARP = BLOCK_N / 2;
+    const int half = e >> 2;      // which slice of the BLOCK_N columns (2 slices with 8 warps, 4 with 16)
+    constexpr int COLS_PER_WARP = BLOCK_N / (EW / 4);
+    constexpr bool LD_AHEAD = EW == 8;      // with 4 warps per scheduler the other warps cover the TMEM latency
     constexpr int NCH = COLS_PER_WARP / 32;
     const uint32_t stg = epi_stage + e * 4096;
     const uint8_t* stg_gen = smem_gen + (stg - smem_base);
@@ -446,7 +457,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       return (tile % num_n_blocks) * BLOCK_N + half * COLS_PER_WARP;
     };
     const bool has_pre = narrow4 || (wide && (e_residual != nullptr || wide_aux));
-    if (has_pre && worker < num_units && tile_n0(worker) < N) {
+    if (LD_AHEAD && has_pre && worker < num_units && tile_n0(worker) < N) {
       prefetch(tile_row0(worker), tile_n0(worker));
       pre_tag = worker * NCH;
     }
@@ -468,6 +479,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       for (int c = 0; c < NCH; ++c) {
         const int n0 = nt0 + 32 * c;
         const bool valid = n0 < N;     // warp-uniform
+        if (!LD_AHEAD && c > 0) tmem_ld_32x32b_x32(t_row + 32 * c, r);
+        // operands of this chunk: already in flight, unless this is a cold start or a 16-warp kernel (no look-ahead)
+        if (valid && has_pre && pre_tag != unit * NCH + c) prefetch(row0, n0);
         float4 bq[8];
         if (valid && ep.bias) {
           const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
@@ -490,7 +504,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         if (c + 1 < NCH) {
-          tmem_ld_32x32b_x32(t_row + 32 * (c + 1), r);       // next chunk, in flight during this chunk's math
+          if (LD_AHEAD) tmem_ld_32x32b_x32(t_row + 32 * (c + 1), r);       // next chunk, in flight during this chunk's math
         } else {
           // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
           tc_fence_before();
@@ -501,11 +515,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
         }
         if (!valid) continue;
-        // operands of this chunk (already in flight unless this is a cold start), and where the next ones come from
-        if (has_pre && pre_tag != unit * NCH + c) prefetch(row0, n0);
+        // where the next chunk's operands come from
         int nunit = unit, nc = c + 1;
         if (nc == NCH) { nunit = unit + num_workers; nc = 0; }
-        const bool nvalid = has_pre && nunit < num_units && tile_n0(nunit) + 32 * nc < N;
+        const bool nvalid = LD_AHEAD && has_pre && nunit < num_units && tile_n0(nunit) + 32 * nc < N;
         const int nrow0 = nvalid ? tile_row0(nunit) : 0, nn0 = nvalid ? tile_n0(nunit) + 32 * nc : 0;
 
         if (n0 < e_col_scale_ncols) {
@@ -615,7 +628,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO, int MODE = EPI_GENERIC>
 int launch(const void* A, long long lda, const void* B, long long ldb, int M, int N, int K, int splits,
            const EpiParams& ep, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, TWO>;
+  using C = Cfg<BLOCK_N, TWO, epi_warps(TWO, MODE)>;
   CUtensorMap tmA, tmB;
   int rc;
   if (!A_MN) rc = make_tmap_2d_bf16(&tmA, A, M, K, lda, BLOCK_M, BLOCK_K);
@@ -640,7 +653,7 @@ int launch(const void* A, long long lda, const void* B, long long ldb, int M, in
   cudaLaunchAttribute attr[1];
   const int workers = min(units, TWO ? num_sms() / 2 : num_sms());
   cfg.gridDim = dim3(TWO ? 2 * workers : workers);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   if (TWO) {
