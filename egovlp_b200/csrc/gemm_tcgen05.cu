@@ -337,8 +337,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   } else if ((warp == 2 || warp == 3) && A_MN && B_MN && !TWO && ep.colsum_a != nullptr) {
     // ===================== column sums of A (wgrad only): bias gradient for free =====================
     // A stage holds A as two slabs [64 k-rows][64 m-columns] (128 B rows, 16-byte chunks XOR-swizzled by row & 7).
-    // Warp 2 sums slab 0, warp 3 slab 1: lane = (row & 3 group, chunk); each lane keeps 8 fp32 column sums.  Only the
-    // units of the first n-block do it, so every (k-range, m-block) is summed exactly once across the grid.
+    // Warp 2 sums slab 0, warp 3 slab 1: lane = (row & 3 group, chunk); each lane keeps 8 fp32 column sums.  The
+    // units of one (k-range, m-block) -- one per n-block, all staging the same A tiles -- share the work: unit n_blk sums
+    // the k-blocks with kb % num_n_blocks == n_blk, so every A tile is summed exactly once across the grid and no unit
+    // carries the whole shared-memory read load (all of it on the n_blk = 0 units cost +25 % on the GEMM).
     const int slab = warp - 2, chunk = lane & 7, rsub = lane >> 3;
     int stage = 0;
     uint32_t phase = 0;
@@ -346,13 +348,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       const int split = unit / num_tiles, tile = unit - split * num_tiles;
       const int m_blk = tile / num_n_blocks, n_blk = tile - m_blk * num_n_blocks;
       const int kb0 = split * kb_per_split, kb1 = min(num_kb, kb0 + kb_per_split);
-      const bool mine = n_blk == 0;
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] = 0.f;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + 8 * stage, phase);
-        if (mine) {
+        if (kb % num_n_blocks == n_blk) {     // this unit's share of the k-blocks
           const uint32_t slab_base = sA + stage * A_STAGE_BYTES + slab * MN_ATOM_BYTES;
 #pragma unroll 4
           for (int i = 0; i < 16; ++i) {
@@ -371,7 +372,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         if (lane == 0) mbar_arrive(empty_bar + 8 * stage);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (mine) {
+      {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
@@ -425,11 +426,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int pre_tag = -1;      // (unit, chunk) whose operands the prefetch registers hold
     auto prefetch = [&](int prow0, int pn0) {
       if (narrow4) {
-        const int grow = min(prow0 + lane, M - 1);
-        const uint4* ap = reinterpret_cast<const uint4*>(e_aux + (long long)grow * ep.ldaux + pn0);
+        // coalesced: 4 lanes cover a row's 64 bytes (8 rows per request); the row-owner layout the multiply needs is
+        // produced by a pass through the staging buffer (one 16-byte load per lane touching 32 different lines cost
+        // the L1 four times the tag lookups)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 t = __ldg(ap + i);
+          const int grow = min(prow0 + 8 * i + (lane >> 2), M - 1);
+          const uint4 t = __ldg(reinterpret_cast<const uint4*>(e_aux + (long long)grow * ep.ldaux + pn0 + (lane & 3) * 8));
           paux[4 * i] = t.x; paux[4 * i + 1] = t.y; paux[4 * i + 2] = t.z; paux[4 * i + 3] = t.w;
         }
       } else if (wide) {
@@ -549,12 +552,28 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 16; ++j) gelu2(gc, v[2 * j], v[2 * j + 1]);
         }
         if (narrow4) {
+          // aux: coalesced registers -> staging half 1 -> this lane's own row
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 f = unpack_bf16x2(paux[j]);
-            up2(mul2(pk2(v[2 * j], v[2 * j + 1]), pk2(f.x, f.y)), v[2 * j], v[2 * j + 1]);
+          for (int i = 0; i < 4; ++i) {
+            const int rl = 8 * i + (lane >> 2), cc = lane & 3;
+            const uint32_t a = stg + rl * 128 + ((((cc ^ ((rl >> 1) & 3)) + 4 * ((rl & 1) ^ 1))) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(paux[4 * i]), "r"(paux[4 * i + 1]),
+                         "r"(paux[4 * i + 2]), "r"(paux[4 * i + 3]));
           }
-          if (nvalid) { prefetch(nrow0, nn0); pre_tag = nunit * NCH + nc; }
+          __syncwarp();
+          if (nvalid) { prefetch(nrow0, nn0); pre_tag = nunit * NCH + nc; }      // registers are free again
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint4 a4 = *reinterpret_cast<const uint4*>(
+                stg_gen + lane * 128 + ((((cc ^ ((lane >> 1) & 3)) + 4 * ((lane & 1) ^ 1))) << 4));
+            const uint32_t w[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = unpack_bf16x2(w[i]);
+              const int j = 4 * cc + i;
+              up2(mul2(pk2(v[2 * j], v[2 * j + 1]), pk2(f.x, f.y)), v[2 * j], v[2 * j + 1]);
+            }
+          }
         }
         if (!wide) {
           stage_bf16_rows(stg, lane, v, 0);
