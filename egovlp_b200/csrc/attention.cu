@@ -1076,12 +1076,12 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     const int r = warp * 4 + (lane >> 3) + i * P0_ROWS;
     const int tok = r < G.NPAD ? row_token_x<RT>(G, g, r, sh) : -1;
     t_pre[i] = tok;
-    o_pre[i] = make_uint4(0, 0, 0, 0);
-    l_pre[i] = 0.f;
-    if (tok >= 0) {
-      o_pre[i] = *reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tok) * G.D + h * HD + (lane & 7) * 8);
-      l_pre[i] = lse_in[((long long)(b * G.H + h)) * G.S + tok] * LOG2E;
-    }
+    // unconditional loads from a clamped row, nothing computed on the values here: a select or a multiply at this point
+    // makes the in-order issue wait for each load before the next one goes out (8 serialised DRAM latencies per CTA --
+    // 28 % of this kernel's stall samples); validity is applied where the values are used
+    const int tc = max(tok, 0);
+    o_pre[i] = __ldg(reinterpret_cast<const uint4*>(out + ((long long)b * G.S + tc) * G.D + h * HD + (lane & 7) * 8));
+    l_pre[i] = __ldg(lse_in + ((long long)(b * G.H + h)) * G.S + tc);
   }
   mbar_wait(sm.bar, 0);
 #pragma unroll
@@ -1103,7 +1103,7 @@ fast_attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_co
     d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
     if (cc == 0) {
       sm.delta[r] = d;
-      sm.lse[r] = l_pre[i];
+      sm.lse[r] = tok >= 0 ? l_pre[i] * LOG2E : 0.f;
     }
   }
   __syncthreads();
