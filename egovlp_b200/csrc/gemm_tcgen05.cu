@@ -167,14 +167,17 @@ __device__ __forceinline__ void stage_bf16_rows(uint32_t stg, int lane, const fl
 __device__ __forceinline__ void store_bf16_coalesced(const uint8_t* stg_gen, int lane, bf16* out, long long ldo, int row0,
                                                      int n0, int M, int which) {
   const int c = lane & 3;
+  uint4 x[4];      // all four shared-memory reads first: a read -> store pair per row made every store wait out a read
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int rl = 8 * i + (lane >> 2), grow = row0 + rl;
-    if (grow < M) {
-      const uint4 x =
-          *reinterpret_cast<const uint4*>(stg_gen + rl * 128 + (((c ^ ((rl >> 1) & 3)) + 4 * ((rl & 1) ^ which)) << 4));
-      *reinterpret_cast<uint4*>(out + (long long)grow * ldo + n0 + c * 8) = x;
-    }
+    const int rl = 8 * i + (lane >> 2);
+    x[i] = *reinterpret_cast<const uint4*>(stg_gen + rl * 128 + (((c ^ ((rl >> 1) & 3)) + 4 * ((rl & 1) ^ which)) << 4));
+  }
+  bf16* p = out + (long long)(row0 + (lane >> 2)) * ldo + n0 + c * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (row0 + 8 * i + (lane >> 2) < M) *reinterpret_cast<uint4*>(p) = x[i];
+    p += 8 * ldo;
   }
 }
 
@@ -464,17 +467,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       prefetch(tile_row0(worker), tile_n0(worker));
       pre_tag = worker * NCH;
     }
+    uint32_t r[32];
+    // wait for accumulator stage of the it-th tile of this CTA and request this warp's first 32 columns of it
+    auto first_chunk = [&](int it_) {
+      const int acc_ = it_ & 1;
+      mbar_wait(tfull_bar + 8 * acc_, (it_ >> 1) & 1);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + acc_ * BLOCK_N + half * COLS_PER_WARP, r);
+    };
+    if (LD_AHEAD && worker < num_units) first_chunk(0);
     int it = 0;
     for (int unit = worker; unit < num_units; unit += num_workers, ++it) {
       const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
       const int row0 = tile_row0(unit);     // first of this warp's 32 rows
       const int nt0 = tile_n0(unit);
       const uint32_t t_row = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + half * COLS_PER_WARP;
-      uint32_t r[32];
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      tmem_ld_32x32b_x32(t_row, r);
+      if (!LD_AHEAD) first_chunk(it);
       // Each chunk: TMEM -> registers in row-owner layout (lane = row, 32 consecutive columns) -> per-column math
       // -> warp-private swizzled smem transpose -> coalesced layout (a row's 64/128 B handled by 4/8 adjacent lanes)
       // -> per-element operands (residual, aux) and full-sector global stores.
@@ -516,6 +524,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             if (TWO && rank != 0) mbar_arrive_remote(mapa_shared(tempty_bar + 8 * acc, 0));
             else mbar_arrive(tempty_bar + 8 * acc);
           }
+          // the first chunk of the next tile travels during this tile's last chunk (its accumulator is normally complete
+          // already: the MMA warp runs one tile ahead of an epilogue that is the bottleneck)
+          if (LD_AHEAD && unit + num_workers < num_units) first_chunk(it + 1);
         }
         if (!valid) continue;
         // where the next chunk's operands come from
