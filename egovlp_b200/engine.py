@@ -7,6 +7,7 @@ Numerics layout: residual stream and LayerNorm statistics in fp32, GEMM operands
 TMEM), attention probabilities never leave the SM, losses in fp32.  fp32 master parameters are the autograd
 leaves; their bf16 GEMM copies come from `Bf16Cache` (refreshed when a parameter's version changes).
 """
+import functools
 import os
 import threading
 import weakref
@@ -221,16 +222,38 @@ def _bf16_of(t32):
     return t16
 
 
-def _split_for(n_out, n_in, k_rows):
+@functools.lru_cache(maxsize=None)
+def _sm_count(device_index):
+    return torch.cuda.get_device_properties(device_index).multi_processor_count
+
+
+@functools.lru_cache(maxsize=None)
+def _split_for(n_out, n_in, k_rows, n_sm=148):
+    """Split-K factor of a weight-gradient GEMM (one persistent CTA per SM, 128 x 256 tiles, 64-row k-blocks): the split
+    whose (tiles x splits) units fill whole waves of the grid.  Cost model = waves x (k-blocks per unit + 4 for the
+    pipeline fill and the atomic epilogue that the next unit cannot hide); the smallest split within 3 % of the best
+    (fewer fp32 atomics).  round(400 / tiles) left the 54-tile qkv gradient at 2.55 waves (378 units on 148 SMs)."""
     tiles = ((n_out + 127) // 128) * ((n_in + 255) // 256)
-    return max(1, min((k_rows + 63) // 64, round(400 / tiles)))
+    num_kb = (k_rows + 63) // 64
+    if os.environ.get("EGOVLP_WGRAD_SPLIT", "waves") == "legacy":       # A/B knob: the round-1 rule
+        return max(1, min(num_kb, round(400 / tiles)))
+    costs = {}
+    for s in range(1, min(num_kb, 64) + 1):
+        kbs = -(-num_kb // s)
+        if -(-num_kb // kbs) != s:          # the kernel drops empty splits: same as a smaller s
+            continue
+        if s > 1 and kbs < 2:
+            break
+        costs[s] = -(-tiles * s // n_sm) * (kbs + 4)
+    floor = min(costs.values())
+    return min(s for s, c in costs.items() if c <= 1.03 * floor)
 
 
 def wgrad(dy16, x16, n_out, n_in, bias_grad=None):
     """dW[n_out, n_in] = dy^T x (contraction over token rows), fp32, split-K atomics.  `bias_grad` (fp32 [n_out],
     zero-initialised) additionally receives colsum(dy), summed from the dy tiles while they are in shared memory."""
     dw = _zeros((n_out, n_in), dy16)
-    ops.gemm(dy16, x16, dw, a_mn=True, b_mn=True, accumulate=True, split_k=_split_for(n_out, n_in, dy16.shape[0]),
+    ops.gemm(dy16, x16, dw, a_mn=True, b_mn=True, accumulate=True, split_k=_split_for(n_out, n_in, dy16.shape[0], _sm_count(dy16.device.index)),
              colsum_a=bias_grad)
     return dw
 
