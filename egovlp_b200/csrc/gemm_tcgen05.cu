@@ -190,6 +190,7 @@ enum EpiMode {
   EPI_ACT3 = 2,      // bias -> GELU -> bf16, GELU' -> bf16 out2                         (Mlp.fc1 forward)
   EPI_MUL_AUX = 3,   // x bf16 aux -> bf16                                               (Mlp.fc2 input gradient)
   EPI_RES_F32 = 4,   // bias + fp32 residual -> fp32                                     (proj / fc2 forward)
+  EPI_ACT1 = 5,      // bias -> GELU -> bf16                                             (Mlp.fc1, inference)
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool TWO, int MODE>
@@ -408,7 +409,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const GeluConsts gc;
     // epilogue fields: compile-time constants in the specialised modes
     constexpr bool GEN = MODE == EPI_GENERIC;
-    const int e_act = GEN ? ep.act : (MODE == EPI_ACT3 ? 3 : MODE == EPI_MUL_AUX ? 4 : 0);
+    const int e_act = GEN ? ep.act : (MODE == EPI_ACT3 ? 3 : MODE == EPI_MUL_AUX ? 4 : MODE == EPI_ACT1 ? 1 : 0);
     const int e_out_mode = GEN ? ep.out_mode : (MODE == EPI_RES_F32 ? 1 : 0);
     const float* e_residual = (GEN || MODE == EPI_RES_F32) ? ep.residual : nullptr;
     const bf16* e_aux = (GEN || MODE == EPI_MUL_AUX) ? ep.aux : nullptr;
@@ -718,6 +719,7 @@ inline int epi_mode(const EpiParams& ep) {
   if (ep.act == 3 && ep.out_mode == 0 && !ep.residual && ep.out2 && no_scale) return EPI_ACT3;
   if (ep.act == 4 && ep.out_mode == 0 && !ep.residual && !ep.out2 && no_scale) return EPI_MUL_AUX;
   if (ep.act == 0 && ep.out_mode == 1 && ep.residual && !ep.out2 && no_scale) return EPI_RES_F32;
+  if (ep.act == 1 && ep.out_mode == 0 && !ep.residual && !ep.out2 && no_scale) return EPI_ACT1;
   return EPI_GENERIC;
 }
 
@@ -774,6 +776,7 @@ extern "C" int egovlp_gemm_bf16(const void* A, int a_mn_major, long long lda, co
       if (mode == EPI_ACT3) { EGOVLP_GEMM_MODE(EPI_ACT3); }
       if (mode == EPI_MUL_AUX) { EGOVLP_GEMM_MODE(EPI_MUL_AUX); }
       if (mode == EPI_RES_F32) { EGOVLP_GEMM_MODE(EPI_RES_F32); }
+      if (mode == EPI_ACT1) { EGOVLP_GEMM_MODE(EPI_ACT1); }
 #undef EGOVLP_GEMM_MODE
     }
     return dispatch_major<256, true>(a_mn_major, b_mn_major, A, lda, B, ldb, M, N, K, split_k, ep, st);

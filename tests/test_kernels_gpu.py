@@ -141,6 +141,8 @@ def test_gemm_specialised_epilogues_match_the_generic_one(ops, monkeypatch, M, N
         ops.gemm(a, wt, o, b_mn=True, aux=aux, act=4); outs.append(o)                                   # EPI_MUL_AUX
         o = torch.empty(M, N, device="cuda", dtype=torch.float32)
         ops.gemm(a, b, o, bias=bias, residual=res); outs.append(o)                                      # EPI_RES_F32
+        o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(a, b, o, bias=bias, act=1); outs.append(o)                                             # EPI_ACT1
         torch.cuda.synchronize()
         return outs
 
@@ -153,6 +155,7 @@ def test_gemm_specialised_epilogues_match_the_generic_one(ops, monkeypatch, M, N
     acc = a.float() @ b.float().t() + bias
     assert rel_err(got[5], acc + res) < 2e-5
     assert rel_err(got[2], torch.nn.functional.gelu(acc)) < 4e-3
+    assert torch.equal(got[6], got[2])             # inference-form GELU == the training form's first output
     assert rel_err(got[4], (a.float() @ wt.float()) * aux.float()) < 4e-3
 
 
