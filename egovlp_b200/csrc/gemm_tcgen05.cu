@@ -12,7 +12,13 @@
 // (dy and x as A and B, contraction over tokens) need -- no transposed copies are ever materialised.
 // One CTA per SM, 128 x BLOCK_N output tile, 64-deep k-blocks, 4-6 stage TMA->smem ring, fp32 accumulators
 // double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..11 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator (2 and 3 also sum the A tiles' columns in
+// the wgrad form), 4..11 = epilogue.  setmaxnreg gives the control warpgroup 64 registers and the epilogue warps 216.
+// Epilogue per warp: 32 rows x BLOCK_N/2 columns in 32-column chunks, software-pipelined (TMEM chunk c+1 and the
+// per-element global operands of chunk c+1 are requested while chunk c is computed; the first chunk of the NEXT tile
+// during the last chunk of this one).  The CTA-pair kernels are additionally instantiated with compile-time specialised
+// epilogues (EpiMode) for the forms that carry the training / inference step; the host picks the mode from the
+// epilogue descriptor, everything else takes the generic epilogue (same arithmetic, same order: bit-identical results).
 #include <stdlib.h>
 
 #include "common.cuh"

@@ -183,3 +183,31 @@ def test_bench_flop_model_matches_the_survey_and_the_oracle_counter():
     want -= 2 * 128 * 256                                     # no projection head in video_tower()
     want -= 2 * 4 * N * 128 * 128 - 2 * 4 * N * 128 * (3 * 16 * 16)   # patch embed of a 16x16x3 patch: K = 768, not D
     assert abs(fc.get_total_flops() - want) / want < 0.02, (fc.get_total_flops(), want)
+
+
+def test_wgrad_split_k_fills_whole_waves(monkeypatch):
+    """engine._split_for: the split-K factor of a weight-gradient GEMM (128 x 256 tiles, 64-row k-blocks, one CTA per SM).
+    At the step's shapes the units must fill >= 95 % of the waves they occupy, the kernel must not have to drop empty
+    splits, and tiny contractions must still spread over the grid; EGOVLP_WGRAD_SPLIT=legacy restores round(400 / tiles)."""
+    from egovlp_b200 import engine
+    monkeypatch.delenv("EGOVLP_WGRAD_SPLIT", raising=False)
+    engine._split_for.cache_clear()
+    n_sm = 148
+    for n_out, n_in in ((2304, 768), (768, 768), (3072, 768), (768, 3072), (256, 768), (768, 256)):
+        for rows in (64 * 3137, 64 * 785, 32 * 3137, 8 * 3137):
+            s = engine._split_for(n_out, n_in, rows, n_sm)
+            tiles = -(-n_out // 128) * -(-n_in // 256)
+            num_kb = -(-rows // 64)
+            assert 1 <= s <= 64
+            kbs = -(-num_kb // s)
+            assert -(-num_kb // kbs) == s                       # no empty splits
+            units = tiles * s
+            assert units / (-(-units // n_sm) * n_sm) >= 0.9, (n_out, n_in, rows, s)
+    # 1024 text tokens: 16 k-blocks only -- still more than one unit per tile
+    assert engine._split_for(768, 768, 1024, n_sm) > 1
+    # the measured case: qkv gradient at 64 clips x 16 frames -> 8 splits (432 units = 2.92 waves), not 7 (2.55 waves)
+    assert engine._split_for(2304, 768, 64 * 3137, n_sm) == 8
+    monkeypatch.setenv("EGOVLP_WGRAD_SPLIT", "legacy")
+    engine._split_for.cache_clear()
+    assert engine._split_for(2304, 768, 64 * 3137, n_sm) == 7
+    engine._split_for.cache_clear()
