@@ -423,16 +423,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     bf16* e_out2 = (GEN || MODE == EPI_ACT3) ? ep.out2 : nullptr;
     const int e_col_scale_ncols = (GEN || MODE == EPI_BF16) ? ep.col_scale_ncols : 0;
     const int e_res_row_mod = GEN ? ep.res_row_mod : 0;
-    // act 4 with a plain bf16 output: multiply in the row-per-lane register domain (4 x 16-byte loads of the lane's own
-    // aux row) and leave through the cheap staged bf16 store -- the "wide" float4 path costs ~3.5x the instructions per
-    // element and made the fc2 input-gradient GEMM epilogue-bound
+    // act 4 with a plain bf16 output: multiply in the row-per-lane register domain (aux fetched coalesced and turned into
+    // the row-owner layout through the staging buffer) and leave through the cheap staged bf16 store -- the "wide" float4
+    // path costs ~3.5x the instructions per element and made the fc2 input-gradient GEMM epilogue-bound
     const bool narrow4 = e_act == 4 && e_out_mode == 0 && e_residual == nullptr && e_colsum == nullptr;
     const bool wide = !narrow4 && (e_out_mode != 0 || e_residual != nullptr || e_act == 2 || e_act == 4 ||
                                    e_colsum != nullptr);
     const bool wide_aux = wide && (e_act == 2 || e_act == 4);
     const int c4 = lane & 7, wr = lane >> 3;         // wide path: lane -> (row within a group of 4, float4 column)
     float4 pres[8];        // prefetched residual (wide path)
-    uint32_t paux[16];     // prefetched aux: 8 x uint2 (wide path) or 4 x uint4 of the lane's own row (narrow4)
+    uint32_t paux[16];     // prefetched aux: 8 x uint2 (wide path) or 4 x uint4 in the coalesced layout (narrow4)
     int pre_tag = -1;      // (unit, chunk) whose operands the prefetch registers hold
     auto prefetch = [&](int prow0, int pn0) {
       if (narrow4) {
