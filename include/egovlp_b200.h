@@ -46,6 +46,9 @@ int egovlp_abi_version(void);
  *          GEMM only multiplies by it);   v += residual[m,n] (fp32);
  *   out_mode 0: out(bf16) = v;  1: out(fp32) = v;  2: atomicAdd(out(fp32), v) (needed for split_k>1)
  * Constraints: N % 32 == 0, lda/ldb/ldo % 8 == 0, 16B-aligned bases.
+ * The library chooses the kernel instance itself (tile scheduler, compile-time specialised epilogue for the common
+ * descriptor forms); every instance computes the arithmetic above in the same order, so the choice never changes a bit of
+ * the result (tests/test_kernels_gpu.py::test_gemm_specialised_epilogues_match_the_generic_one).
  */
 typedef struct egovlp_gemm_epilogue {
   const float* bias;     /* [N] fp32 or NULL */
